@@ -1,0 +1,379 @@
+"""CPU oracle for the KARIOS KLT matching hot path (numpy + oracle/klt_oracle.c).
+
+TEST INFRASTRUCTURE ONLY: imported by tests/, __graft_entry__.smoke() and
+bench.py's cpu_baseline / --impl reference legs, never by karios_b200/.
+
+Mirrors the reference call structure so that parity tests read like the
+reference's own:
+  to_uint8            <- karios/matcher/klt.py:42-49   (_to_uint8)
+  laplacian           <- klt.py:433-434                 (cv2.Laplacian(u8, CV_8U, k))
+  auto_mask           <- klt.py:268-276
+  good_features       <- klt.py:120                     (cv2.goodFeaturesToTrack)
+  pyr_lk              <- klt.py:134-140                 (cv2.calcOpticalFlowPyrLK)
+  klt_tracker         <- klt.py:83-172
+  match_tile / match  <- klt.py:198-349 (default + dict ksize, fixed polarity)
+  zncc                <- karios/matcher/zncc_service.py:162-238, 45-126
+
+Parity pinning: tests/golden/*.npz were produced by the UNMODIFIED reference
+modules running against cv2 4.13.0 (oracle/make_golden.py); tests/test_oracle.py
+checks every function here against them (and against cv2 directly when cv2 is
+importable).
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+from dataclasses import dataclass
+from typing import Optional
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "libklt_oracle.so")
+_lib = None
+
+
+def build(force: bool = False) -> str:
+    """Compile oracle/klt_oracle.c (gcc, see oracle/Makefile)."""
+    src = os.path.join(_HERE, "klt_oracle.c")
+    if force or not os.path.exists(_LIB_PATH) or os.path.getmtime(_LIB_PATH) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-C", _HERE, "-B", "libklt_oracle.so"],
+                              stdout=subprocess.DEVNULL)
+    return _LIB_PATH
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_LIB_PATH):
+            build()
+        L = ctypes.CDLL(_LIB_PATH)
+        c = ctypes
+        vp, i32, i64, f64 = c.c_void_p, c.c_int, c.c_int64, c.c_double
+        L.orc_minmax_u16.argtypes = [vp, i64, vp, vp]
+        L.orc_minmax_u16.restype = None
+        L.orc_to_uint8_u16.argtypes = [vp, i64, f64, f64, vp]
+        L.orc_to_uint8_u16.restype = None
+        L.orc_auto_mask_u16.argtypes = [vp, vp, i64, i32, f64, i32, f64, vp]
+        L.orc_auto_mask_u16.restype = i64
+        L.orc_laplacian_u8.argtypes = [vp, i32, i32, i32, vp]
+        L.orc_laplacian_u8.restype = i32
+        L.orc_min_eigen_val.argtypes = [vp, i32, i32, i32, i32, vp]
+        L.orc_min_eigen_val.restype = i32
+        L.orc_select_corners.argtypes = [vp, vp, i32, i32, i32, f64, f64, vp, i64, vp, vp]
+        L.orc_select_corners.restype = i64
+        L.orc_pyr_down_u8.argtypes = [vp, i32, i32, vp]
+        L.orc_pyr_down_u8.restype = None
+        L.orc_pyr_lk.argtypes = [vp, vp, i32, i32, vp, i64, i32, i32, i32, f64, f64, i32, vp, vp, vp]
+        L.orc_pyr_lk.restype = i32
+        L.orc_zncc_u16.argtypes = [vp, i32, i32, vp, i32, i32, vp, vp, vp, vp, i64, vp]
+        L.orc_zncc_u16.restype = None
+        _lib = L
+    return _lib
+
+
+def _p(a: np.ndarray):
+    return a.ctypes.data_as(ctypes.c_void_p)
+
+
+def _c(a, dtype):
+    return np.ascontiguousarray(a, dtype=dtype)
+
+
+# --------------------------------------------------------------------------- a4
+def to_uint8(arr: np.ndarray) -> np.ndarray:
+    """klt.py:42-49.  uint8 is a no-op; uint16 uses the C path; anything else the
+    literal numpy expression of the reference."""
+    if arr.dtype == np.uint8:
+        return arr
+    if arr.dtype == np.uint16:
+        a = _c(arr, np.uint16)
+        mn, mx = ctypes.c_double(), ctypes.c_double()
+        lib().orc_minmax_u16(_p(a), a.size, ctypes.byref(mn), ctypes.byref(mx))
+        out = np.empty(a.shape, np.uint8)
+        lib().orc_to_uint8_u16(_p(a), a.size, mn.value, mx.value, _p(out))
+        return out
+    arr_min, arr_max = float(np.nanmin(arr)), float(np.nanmax(arr))
+    if arr_max > arr_min:
+        return ((arr - arr_min) / (arr_max - arr_min) * 255).astype(np.uint8)
+    return np.zeros_like(arr, dtype=np.uint8)
+
+
+def to_uint8_lut(mn: float, mx: float) -> np.ndarray:
+    """The 65 536-entry table the uint16 path is equivalent to."""
+    v = np.arange(65536, dtype=np.uint16)
+    if not mx > mn:
+        return np.zeros(65536, np.uint8)
+    with np.errstate(invalid="ignore"):
+        q = (v - float(mn)) / (float(mx) - float(mn)) * 255
+    out = np.zeros(65536, np.uint8)
+    ok = (q >= 0) & (q < 256)
+    out[ok] = q[ok].astype(np.uint8)
+    return out
+
+
+# --------------------------------------------------------------------------- a3
+def auto_mask(mon: np.ndarray, ref: np.ndarray, nd_mon=None, nd_ref=None):
+    """klt.py:268-276 -> (uint8 mask, valid pixel count)."""
+    if mon.dtype == np.uint16 and ref.dtype == np.uint16:
+        m, r = _c(mon, np.uint16), _c(ref, np.uint16)
+        mask = np.empty(m.shape, np.uint8)
+        cnt = lib().orc_auto_mask_u16(_p(m), _p(r), m.size,
+                                      int(nd_mon is not None), float(nd_mon or 0),
+                                      int(nd_ref is not None), float(nd_ref or 0), _p(mask))
+        return mask, int(cnt)
+    mask = (mon != 0) & (ref != 0) & np.isfinite(ref) & np.isfinite(mon)
+    if nd_mon is not None:
+        mask &= mon != nd_mon
+    if nd_ref is not None:
+        mask &= ref != nd_ref
+    mask = mask.astype(np.uint8)
+    return mask, int(np.count_nonzero(mask))
+
+
+# --------------------------------------------------------------------------- a6
+def laplacian(u8: np.ndarray, ksize: int) -> np.ndarray:
+    """cv2.Laplacian(u8, cv2.CV_8U, ksize=ksize) (klt.py:433-434)."""
+    src = _c(u8, np.uint8)
+    h, w = src.shape
+    dst = np.empty_like(src)
+    rc = lib().orc_laplacian_u8(_p(src), w, h, int(ksize), _p(dst))
+    if rc:
+        raise ValueError(f"unsupported Laplacian ksize {ksize}")
+    return dst
+
+
+# --------------------------------------------------------------------------- a7
+def cv_tail_start(w: int) -> int:
+    """First column of the non-FMA Sobel row-filter tail in the cv2 4.13 AVX-512
+    build."""
+    return 32 * (w // 32)
+
+
+def min_eigen_val(u8: np.ndarray, block: int, tail_start: Optional[int] = None) -> np.ndarray:
+    src = _c(u8, np.uint8)
+    h, w = src.shape
+    eig = np.empty((h, w), np.float32)
+    ts = cv_tail_start(w) if tail_start is None else tail_start
+    rc = lib().orc_min_eigen_val(_p(src), w, h, int(block), int(ts), _p(eig))
+    if rc:
+        raise MemoryError("orc_min_eigen_val")
+    return eig
+
+
+def select_corners(eig: np.ndarray, mask, max_corners: int, quality: float, min_distance: float):
+    e = _c(eig, np.float32)
+    h, w = e.shape
+    m = None if mask is None else _c(mask, np.uint8)
+    cap = (w * h) if max_corners <= 0 else max_corners
+    cap = min(cap, max(1, (w * h)))
+    out = np.empty((cap, 2), np.float32)
+    ncand = ctypes.c_int64()
+    mval = ctypes.c_float()
+    n = lib().orc_select_corners(_p(e), None if m is None else _p(m), w, h, int(max_corners),
+                                 float(quality), float(min_distance), _p(out), cap,
+                                 ctypes.byref(ncand), ctypes.byref(mval))
+    if n < 0:
+        raise MemoryError("orc_select_corners")
+    return out[:n].copy(), int(ncand.value), float(mval.value)
+
+
+def good_features(u8, mask, max_corners, quality, min_distance, block, tail_start=None):
+    """cv2.goodFeaturesToTrack(...) -> [N,1,2] float32 or None (klt.py:120)."""
+    eig = min_eigen_val(u8, block, tail_start)
+    pts, _, _ = select_corners(eig, mask, max_corners, quality, min_distance)
+    if len(pts) == 0:
+        return None
+    return pts.reshape(-1, 1, 2)
+
+
+# --------------------------------------------------------------------------- a8
+def pyr_down(u8: np.ndarray) -> np.ndarray:
+    src = _c(u8, np.uint8)
+    h, w = src.shape
+    dst = np.empty(((h + 1) // 2, (w + 1) // 2), np.uint8)
+    lib().orc_pyr_down_u8(_p(src), w, h, _p(dst))
+    return dst
+
+
+def pyr_lk(prev, nxt, p0, win=25, max_level=1, max_count=30, eps=0.03, min_eig=1e-4,
+           acc_mode=0):
+    """cv2.calcOpticalFlowPyrLK(prev, next, p0, None, winSize=(win,win), maxLevel,
+    criteria=(EPS|COUNT, max_count, eps)) -> (p1 [N,1,2], status [N,1] u8, err [N,1])."""
+    a, b = _c(prev, np.uint8), _c(nxt, np.uint8)
+    h, w = a.shape
+    pts = _c(np.asarray(p0).reshape(-1, 2), np.float32)
+    n = len(pts)
+    out = np.empty((n, 2), np.float32)
+    st = np.empty(n, np.uint8)
+    err = np.empty(n, np.float32)
+    lib().orc_pyr_lk(_p(a), _p(b), w, h, _p(pts), n, int(win), int(max_level), int(max_count),
+                     float(eps), float(min_eig), int(acc_mode), _p(out), _p(st), _p(err))
+    return out.reshape(-1, 1, 2), st.reshape(-1, 1), err.reshape(-1, 1)
+
+
+# --------------------------------------------------------------------------- a13
+@dataclass
+class KLTConfiguration:
+    """Field-for-field mirror of karios/core/configuration.py:36-50."""
+    minDistance: int = 10
+    blocksize: int = 15
+    maxCorners: int = 20000
+    matching_winsize: int = 25
+    qualityLevel: float = 0.1
+    xStart: int = 0
+    tile_size: int = 20000
+    laplacian_kernel_size: object = 7
+    outliers_filtering: bool = False
+    laplacian_invert_polarity: object = False
+
+
+def filter_outliers(x0, y0, x1, y1, score):
+    """klt.py:52-71."""
+    dx = x1 - x0
+    dy = y1 - y0
+    while True:
+        ind = ((np.abs(dx - dx.mean()) < 3 * dx.std()) & (np.abs(dy - dy.mean()) < 3 * dy.std())
+               & (np.abs(dx - dx.mean()) < 20) & (np.abs(dy - dy.mean()) < 20))
+        if ind.sum() == len(dx):
+            break
+        dx, dy, x0, x1, y0, y1, score = dx[ind], dy[ind], x0[ind], x1[ind], y0[ind], y1[ind], score[ind]
+    return x0, y0, x1, y1, score
+
+
+def klt_tracker(ref_data, image_data, mask, conf, p0=None, acc_mode=0):
+    """klt.py:83-172 -> (dict of float32 columns x0,y0,dx,dy,score, Ninit) or None."""
+    if p0 is None:
+        p0 = good_features(ref_data, mask, conf.maxCorners, conf.qualityLevel, conf.minDistance,
+                           conf.blocksize)
+    if p0 is None:
+        return None
+    w = conf.matching_winsize
+    p1, _, _ = pyr_lk(ref_data, image_data, p0, win=w, acc_mode=acc_mode)
+    p0r, _, _ = pyr_lk(image_data, ref_data, p1, win=w, acc_mode=acc_mode)
+    d = np.abs(p0 - p0r).reshape(-1, 2).max(-1)
+    st = d < 0.1
+    ninit = len(p0)
+    p0k, p1k, dk = p0[st], p1[st], d[st]
+    score = 1 - dk / 0.1
+    x0, y0 = p0k[:, 0, 0], p0k[:, 0, 1]
+    x1, y1 = p1k[:, 0, 0], p1k[:, 0, 1]
+    if conf.outliers_filtering and len(x0):
+        x0, y0, x1, y1, score = filter_outliers(x0, y0, x1, y1, score)
+    cols = {"x0": x0, "y0": y0, "dx": x1 - x0, "dy": y1 - y0, "score": score.astype(np.float32)}
+    return cols, ninit
+
+
+def _ksizes(conf):
+    k = conf.laplacian_kernel_size
+    if isinstance(k, dict):
+        return k.get("mon", k.get("ref", 1)), k.get("ref", k.get("mon", 1))
+    return k, k
+
+
+def match_tile(mon_box, ref_box, mask_box, conf, x_off=0, y_off=0, nd_mon=None, nd_ref=None,
+               acc_mode=0):
+    """klt.py:236-349 for int / dict ksize and fixed polarity.  Returns the dict of
+    columns sorted by (x0, y0) with tile offsets applied, or None."""
+    if mask_box is None:
+        mask_box, valid = auto_mask(mon_box, ref_box, nd_mon, nd_ref)
+    else:
+        valid = int(np.count_nonzero(mask_box > 0))
+    if valid == 0:
+        return None
+    mk, rk = _ksizes(conf)
+    mon_u8 = to_uint8(mon_box)
+    if conf.laplacian_invert_polarity is True:
+        mon_u8 = 255 - mon_u8
+    lap_mon = laplacian(mon_u8, mk)
+    lap_ref = laplacian(to_uint8(ref_box), rk)
+    res = klt_tracker(lap_ref, lap_mon, mask_box, conf, acc_mode=acc_mode)
+    if res is None:
+        return None
+    cols, ninit = res
+    cols["x0"] = cols["x0"] + np.float32(x_off)
+    cols["y0"] = cols["y0"] + np.float32(y_off)
+    order = np.lexsort((cols["y0"], cols["x0"]))
+    cols = {k: v[order] for k, v in cols.items()}
+    cols["ninit"] = ninit
+    return cols
+
+
+def tile_boxes(x_size, y_size, conf):
+    """Tile enumeration of KLT.match (klt.py:221-249): x outer, y inner."""
+    out = []
+    for x_off in range(0, x_size, conf.tile_size):
+        if x_off < conf.xStart:
+            continue
+        for y_off in range(0, y_size, conf.tile_size):
+            xs = conf.tile_size if x_off + conf.tile_size < x_size else x_size - x_off
+            ys = conf.tile_size if y_off + conf.tile_size < y_size else y_size - y_off
+            out.append((x_off, y_off, xs, ys))
+    return out
+
+
+def match(mon, ref, mask, conf, nd_mon=None, nd_ref=None, acc_mode=0):
+    """KLT.match over whole arrays: list of per-tile column dicts."""
+    h, w = mon.shape
+    res = []
+    for (xo, yo, xs, ys) in tile_boxes(w, h, conf):
+        mb = None if mask is None else mask[yo:yo + ys, xo:xo + xs]
+        r = match_tile(mon[yo:yo + ys, xo:xo + xs], ref[yo:yo + ys, xo:xo + xs], mb, conf, xo, yo,
+                       nd_mon, nd_ref, acc_mode)
+        if r is not None:
+            res.append(r)
+    return res
+
+
+# --------------------------------------------------------------------------- a12
+def zncc(x0, y0, dx, dy, monitored: np.ndarray, reference: np.ndarray) -> np.ndarray:
+    """ZNCCService.compute_zncc over float32 columns (zncc_service.py:162-238):
+    float64 scores, NaN where the reference yields NaN."""
+    n = len(x0)
+    out = np.empty(n, np.float64)
+    if monitored.dtype == np.uint16 and reference.dtype == np.uint16:
+        m, r = _c(monitored, np.uint16), _c(reference, np.uint16)
+        a = [_c(v, np.float32) for v in (x0, y0, dx, dy)]
+        lib().orc_zncc_u16(_p(r), r.shape[1], r.shape[0], _p(m), m.shape[1], m.shape[0],
+                           _p(a[0]), _p(a[1]), _p(a[2]), _p(a[3]), n, _p(out))
+        return out
+    # generic dtype: literal restatement of _compute_zncc / _zncc2
+    for i in range(n):
+        out[i] = _zncc_one(np.float32(x0[i]), np.float32(y0[i]), np.float32(dx[i]),
+                           np.float32(dy[i]), monitored, reference)
+    return out
+
+
+def zncc2(img1, img2, u1, v1, u2, v2, n):
+    """_zncc2 (zncc_service.py:45-126)."""
+    if n < 0:
+        raise ValueError("Window half-size n must be non-negative")
+    h1, w1 = img1.shape
+    h2, w2 = img2.shape
+    if (u1 - n < 0 or u1 + n >= h1 or v1 - n < 0 or v1 + n >= w1
+            or u2 - n < 0 or u2 + n >= h2 or v2 - n < 0 or v2 + n >= w2):
+        raise IndexError("Patch window extends beyond image boundaries")
+    p1 = img1[u1 - n:u1 + n + 1, v1 - n:v1 + n + 1]
+    p2 = img2[u2 - n:u2 + n + 1, v2 - n:v2 + n + 1]
+    s1, s2 = float(np.std(p1)), float(np.std(p2))
+    if s1 == 0 or s2 == 0:
+        return np.nan
+    return float(np.mean(((p1 - np.mean(p1)) / s1) * ((p2 - np.mean(p2)) / s2)))
+
+
+def _zncc_one(x0f, y0f, dxf, dyf, monitored, reference):
+    m = 28
+    x0, y0 = int(x0f), int(y0f)
+    x1, y1 = round(x0f + dxf), round(y0f + dyf)
+    if x0 - m < 0 or y0 - m < 0 or x1 - m < 0 or y1 - m < 0:
+        return np.nan
+    if (x0 >= reference.shape[1] - m or y0 >= reference.shape[0] - m
+            or x1 >= monitored.shape[1] - m or y1 >= monitored.shape[0] - m):
+        return np.nan
+    cr = reference[y0 - m:y0 + m + 1, x0 - m:x0 + m + 1]
+    cm = monitored[y1 - m:y1 + m + 1, x1 - m:x1 + m + 1]
+    try:
+        return zncc2(cr, cm, 28, 28, 28, 28, 21)
+    except Exception:  # noqa: BLE001 - mirrors zncc_service.py:232-238
+        return np.nan
