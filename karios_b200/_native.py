@@ -1,0 +1,366 @@
+"""ctypes binding of libkarios_b200.so (C ABI: include/karios_b200.h).
+
+There is NO fallback: if the CUDA library is missing or no CUDA device is
+present, importing / using this module raises.  PyTorch is used only for device
+memory and streams.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+
+import numpy as np
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "_lib", "libkarios_b200.so")
+
+KR_U8, KR_U16, KR_I16, KR_F32 = 0, 1, 2, 3
+KR_TAIL_NONE, KR_TAIL_AVX512 = 0, 32
+
+EXPORTS = [
+    "kr_version", "kr_last_error", "kr_ctx_create", "kr_ctx_destroy", "kr_read_stats",
+    "kr_set_select_all", "kr_minmax_mask", "kr_u8_laplacian", "kr_corner_min_eigen_val",
+    "kr_good_features", "kr_pyr_down", "kr_pyr_lk", "kr_klt_track", "kr_zncc", "kr_match_tile",
+]
+
+
+class KltConf(C.Structure):
+    _fields_ = [("max_corners", C.c_int32), ("block_size", C.c_int32), ("win_size", C.c_int32),
+                ("max_level", C.c_int32), ("max_count", C.c_int32), ("ksize_mon", C.c_int32),
+                ("ksize_ref", C.c_int32), ("invert_mon", C.c_int32), ("tail_mode", C.c_int32),
+                ("compute_zncc", C.c_int32), ("quality_level", C.c_double),
+                ("min_distance", C.c_double), ("eps", C.c_double),
+                ("min_eig_threshold", C.c_double), ("back_threshold", C.c_double),
+                ("zncc_min_score", C.c_double)]
+
+
+class Stats(C.Structure):
+    _fields_ = [("min_a", C.c_double), ("max_a", C.c_double), ("min_b", C.c_double),
+                ("max_b", C.c_double), ("valid", C.c_uint64), ("eig_max", C.c_float),
+                ("n_candidates", C.c_uint32), ("n_above_threshold", C.c_uint32),
+                ("n_sorted", C.c_uint32), ("n_corners", C.c_uint32), ("n_kept", C.c_uint32),
+                ("nms_rounds", C.c_uint32), ("overflow", C.c_uint32),
+                ("select_incomplete", C.c_uint32)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+class Rows(C.Structure):
+    _fields_ = [("x0", C.c_void_p), ("y0", C.c_void_p), ("dx", C.c_void_p), ("dy", C.c_void_p),
+                ("score", C.c_void_p), ("zncc", C.c_void_p), ("capacity", C.c_int32)]
+
+
+_lib = None
+_lib_lock = threading.Lock()
+
+
+class KariosB200Error(RuntimeError):
+    pass
+
+
+def load_library(path: str = LIB_PATH):
+    """dlopen the C-ABI library and declare every prototype."""
+    global _lib
+    with _lib_lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.exists(path):
+            raise KariosB200Error(
+                f"{path} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(nvcc, sm_100a).  karios_b200 has no CPU fallback.")
+        L = C.CDLL(path)
+        vp, i32, i64, f64 = C.c_void_p, C.c_int, C.c_int64, C.c_double
+        L.kr_version.restype = i32
+        L.kr_last_error.restype = C.c_char_p
+        L.kr_ctx_create.argtypes = [i32, i32, i32, i32, C.POINTER(vp)]
+        L.kr_ctx_destroy.argtypes = [vp]
+        L.kr_ctx_destroy.restype = None
+        L.kr_read_stats.argtypes = [vp, vp, C.POINTER(Stats)]
+        L.kr_set_select_all.argtypes = [vp, i32]
+        L.kr_minmax_mask.argtypes = [vp, vp, i64, vp, i64, i32, i32, i32, i32, f64, i32, f64, vp, i64, vp]
+        L.kr_u8_laplacian.argtypes = [vp, vp, i64, i32, i32, i32, i32, i32, i32, vp, i64, vp]
+        L.kr_corner_min_eigen_val.argtypes = [vp, vp, i64, i32, i32, i32, i32, vp, i64, vp]
+        L.kr_good_features.argtypes = [vp, vp, i64, vp, i64, i32, i32, i32, f64, f64, i32, i32, vp,
+                                       i32, vp, vp]
+        L.kr_pyr_down.argtypes = [vp, vp, i64, i32, i32, vp, i64, vp]
+        L.kr_pyr_lk.argtypes = [vp, vp, i64, vp, i64, i32, i32, vp, i32, vp, i32, i32, i32, f64, f64,
+                                vp, vp, vp, vp]
+        L.kr_klt_track.argtypes = [vp, vp, i64, vp, i64, vp, i64, i32, i32, C.POINTER(KltConf), vp,
+                                   i32, Rows, vp]
+        L.kr_zncc.argtypes = [vp, vp, i64, i32, i32, vp, i64, i32, i32, i32, vp, vp, vp, vp, i32, vp,
+                              vp, vp]
+        L.kr_match_tile.argtypes = [vp, vp, i64, vp, i64, i32, i32, i32, vp, i64, i32, i32, i32, i32,
+                                    i32, f64, i32, f64, C.POINTER(KltConf), Rows, vp]
+        for name in EXPORTS:
+            if name not in ("kr_last_error", "kr_ctx_destroy", "kr_version"):
+                getattr(L, name).restype = i32
+        _lib = L
+        return L
+
+
+def _check(rc: int):
+    if rc != 0:
+        msg = load_library().kr_last_error().decode("utf-8", "replace")
+        raise KariosB200Error(f"karios_b200 error {rc}: {msg}")
+
+
+_DTYPES = {torch.uint8: KR_U8, torch.uint16: KR_U16, torch.int16: KR_I16, torch.float32: KR_F32}
+
+
+def dtype_code(t: torch.Tensor) -> int:
+    try:
+        return _DTYPES[t.dtype]
+    except KeyError:
+        raise KariosB200Error(f"raster dtype {t.dtype} not supported (uint8, uint16, int16, float32)")
+
+
+def to_device(a, device) -> torch.Tensor:
+    """numpy array / torch tensor -> 2-D CUDA tensor with unit column stride."""
+    if isinstance(a, torch.Tensor):
+        t = a
+    else:
+        a = np.asarray(a)
+        if a.dtype == np.bool_:
+            a = a.astype(np.uint8)
+        t = torch.from_numpy(np.ascontiguousarray(a))
+    if t.device.type != "cuda":
+        t = t.to(device, non_blocking=True)
+    if t.dim() != 2:
+        raise KariosB200Error(f"expected a 2-D raster, got shape {tuple(t.shape)}")
+    if t.stride(1) != 1:
+        t = t.contiguous()
+    return t
+
+
+def _pitch(t: torch.Tensor) -> int:
+    return t.stride(0) * t.element_size()
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def make_conf(conf, ksize_mon=None, ksize_ref=None, invert_mon=None, tail_mode=KR_TAIL_AVX512,
+              compute_zncc=False, zncc_min_score=0.4) -> KltConf:
+    """KLTConfiguration (karios/core/configuration.py:36-50) + the constants of
+    klt.py:128-132,143 -> kr_klt_conf."""
+    k = conf.laplacian_kernel_size
+    if isinstance(k, dict):
+        km = k.get("mon", k.get("ref", 1))
+        kr = k.get("ref", k.get("mon", 1))
+    elif isinstance(k, str):
+        km = kr = 0          # "auto": the caller supplies explicit sizes
+    else:
+        km = kr = int(k)
+    inv = conf.laplacian_invert_polarity
+    c = KltConf()
+    c.max_corners = int(conf.maxCorners)
+    c.block_size = int(conf.blocksize)
+    c.win_size = int(conf.matching_winsize)
+    c.max_level = 1
+    c.max_count = 30
+    c.ksize_mon = int(km if ksize_mon is None else ksize_mon)
+    c.ksize_ref = int(kr if ksize_ref is None else ksize_ref)
+    c.invert_mon = int(bool(inv) if invert_mon is None and inv != "auto" else bool(invert_mon))
+    c.tail_mode = int(tail_mode)
+    c.compute_zncc = int(bool(compute_zncc))
+    c.quality_level = float(conf.qualityLevel)
+    c.min_distance = float(conf.minDistance)
+    c.eps = 0.03
+    c.min_eig_threshold = 1e-4
+    c.back_threshold = 0.1
+    c.zncc_min_score = float(zncc_min_score)
+    return c
+
+
+class RowBuffers:
+    """Device SoA for the rows of one tile (kr_rows)."""
+
+    def __init__(self, capacity: int, device, with_zncc=True):
+        self.capacity = int(capacity)
+        self.f32 = torch.empty((5, self.capacity), dtype=torch.float32, device=device)
+        self.zncc = torch.empty(self.capacity, dtype=torch.float64, device=device) if with_zncc else None
+
+    def struct(self) -> Rows:
+        r = Rows()
+        base, step = self.f32.data_ptr(), self.capacity * 4
+        r.x0, r.y0, r.dx, r.dy, r.score = (base + i * step for i in range(5))
+        r.zncc = self.zncc.data_ptr() if self.zncc is not None else None
+        r.capacity = self.capacity
+        return r
+
+
+class Context:
+    """One kr_ctx: scratch for tiles up to max_w x max_h on one device.  Not
+    thread-safe (one per host thread)."""
+
+    def __init__(self, max_w: int, max_h: int, max_corners: int, device=None):
+        if not torch.cuda.is_available():
+            raise KariosB200Error("no CUDA device: karios_b200 has no CPU fallback")
+        self.lib = load_library()
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None \
+            else torch.device(device)
+        self.max_w, self.max_h, self.max_corners = int(max_w), int(max_h), int(max_corners)
+        h = C.c_void_p()
+        with torch.cuda.device(self.device):
+            _check(self.lib.kr_ctx_create(self.device.index or 0, self.max_w, self.max_h,
+                                          self.max_corners, C.byref(h)))
+        self._h = h
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self.lib.kr_ctx_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # noqa: BLE001
+            pass
+
+    def fits(self, w, h, max_corners):
+        return w <= self.max_w and h <= self.max_h and (
+            (max_corners <= 0 and self.max_corners <= 0) or
+            (0 < max_corners <= self.max_corners) or (max_corners > 0 and self.max_corners <= 0))
+
+    # ---- thin wrappers, one per C entry point --------------------------------
+    def read_stats(self) -> Stats:
+        s = Stats()
+        _check(self.lib.kr_read_stats(self._h, _stream(), C.byref(s)))
+        if s.overflow:
+            raise KariosB200Error("candidate list overflowed the context capacity "
+                                  "(create the Context for a larger tile)")
+        return s
+
+    def set_select_all(self, on: bool):
+        _check(self.lib.kr_set_select_all(self._h, int(bool(on))))
+
+    def minmax_mask(self, a, b=None, nodata_a=None, nodata_b=None, want_mask=False):
+        h, w = a.shape
+        mask = torch.empty((h, w), dtype=torch.uint8, device=a.device) if want_mask else None
+        _check(self.lib.kr_minmax_mask(
+            self._h, a.data_ptr(), _pitch(a), b.data_ptr() if b is not None else None,
+            _pitch(b) if b is not None else 0, dtype_code(a), w, h,
+            int(nodata_a is not None), float(nodata_a or 0), int(nodata_b is not None),
+            float(nodata_b or 0), mask.data_ptr() if want_mask else None, w if want_mask else 0,
+            _stream()))
+        return mask
+
+    def u8_laplacian(self, img, ksize, invert=False, slot=-1, out=None):
+        h, w = img.shape
+        if out is None:
+            out = torch.empty((h, w), dtype=torch.uint8, device=img.device)
+        _check(self.lib.kr_u8_laplacian(self._h, img.data_ptr(), _pitch(img), dtype_code(img), w, h,
+                                        int(slot), int(ksize), int(bool(invert)), out.data_ptr(),
+                                        _pitch(out), _stream()))
+        return out
+
+    def corner_min_eigen_val(self, u8, block, tail_mode=KR_TAIL_AVX512):
+        h, w = u8.shape
+        eig = torch.empty((h, w), dtype=torch.float32, device=u8.device)
+        _check(self.lib.kr_corner_min_eigen_val(self._h, u8.data_ptr(), _pitch(u8), w, h, int(block),
+                                                int(tail_mode), eig.data_ptr(), _pitch(eig), _stream()))
+        return eig
+
+    def good_features(self, u8, mask, max_corners, quality, min_distance, block,
+                      tail_mode=KR_TAIL_AVX512):
+        """-> CUDA tensor [N, 2] float32 in OpenCV order (N may be 0)."""
+        h, w = u8.shape
+        cap = int(max_corners) if max_corners > 0 else max(1, min(w * h, self._cap_unlimited(w, h)))
+        out = torch.empty((cap, 2), dtype=torch.float32, device=u8.device)
+        cnt = torch.zeros(1, dtype=torch.int32, device=u8.device)
+        for attempt in range(2):
+            _check(self.lib.kr_good_features(
+                self._h, u8.data_ptr(), _pitch(u8), mask.data_ptr() if mask is not None else None,
+                _pitch(mask) if mask is not None else 0, w, h, int(max_corners), float(quality),
+                float(min_distance), int(block), int(tail_mode), out.data_ptr(), cap, cnt.data_ptr(),
+                _stream()))
+            st = self.read_stats()
+            if not st.select_incomplete or attempt == 1:
+                break
+            self.set_select_all(True)
+        self.set_select_all(False)
+        return out[: int(st.n_corners)]
+
+    def _cap_unlimited(self, w, h):
+        p = self.max_w * self.max_h
+        return max(p // 8, 65536)
+
+    def pyr_down(self, u8):
+        h, w = u8.shape
+        out = torch.empty(((h + 1) // 2, (w + 1) // 2), dtype=torch.uint8, device=u8.device)
+        _check(self.lib.kr_pyr_down(self._h, u8.data_ptr(), _pitch(u8), w, h, out.data_ptr(),
+                                    _pitch(out), _stream()))
+        return out
+
+    def pyr_lk(self, prev, nxt, p0, win=25, max_level=1, max_count=30, eps=0.03, min_eig=1e-4):
+        h, w = prev.shape
+        p0 = p0.reshape(-1, 2).contiguous()
+        n = p0.shape[0]
+        p1 = torch.empty_like(p0)
+        st = torch.empty(n, dtype=torch.uint8, device=p0.device)
+        err = torch.empty(n, dtype=torch.float32, device=p0.device)
+        if n:
+            _check(self.lib.kr_pyr_lk(self._h, prev.data_ptr(), _pitch(prev), nxt.data_ptr(),
+                                      _pitch(nxt), w, h, p0.data_ptr(), n, None, int(win),
+                                      int(max_level), int(max_count), float(eps), float(min_eig),
+                                      p1.data_ptr(), st.data_ptr(), err.data_ptr(), _stream()))
+        return p1, st, err
+
+    def klt_track(self, ref_u8, mon_u8, mask, kconf: KltConf, rows: RowBuffers, p0=None):
+        """-> (n_init, n_kept) after one synchronisation."""
+        h, w = ref_u8.shape
+        n_p0 = 0
+        if p0 is not None:
+            p0 = p0.reshape(-1, 2).contiguous()
+            n_p0 = p0.shape[0]
+        for attempt in range(2):
+            _check(self.lib.kr_klt_track(
+                self._h, ref_u8.data_ptr(), _pitch(ref_u8), mon_u8.data_ptr(), _pitch(mon_u8),
+                mask.data_ptr() if mask is not None else None,
+                _pitch(mask) if mask is not None else 0, w, h, C.byref(kconf),
+                p0.data_ptr() if p0 is not None else None, n_p0, rows.struct(), _stream()))
+            st = self.read_stats()
+            if p0 is not None or not st.select_incomplete or attempt == 1:
+                break
+            self.set_select_all(True)
+        self.set_select_all(False)
+        return int(st.n_corners), int(st.n_kept)
+
+    def zncc(self, ref, mon, x0, y0, dx, dy):
+        n = x0.shape[0]
+        out = torch.empty(n, dtype=torch.float64, device=ref.device)
+        if n:
+            _check(self.lib.kr_zncc(self._h, ref.data_ptr(), _pitch(ref), ref.shape[1], ref.shape[0],
+                                    mon.data_ptr(), _pitch(mon), mon.shape[1], mon.shape[0],
+                                    dtype_code(ref), x0.data_ptr(), y0.data_ptr(), dx.data_ptr(),
+                                    dy.data_ptr(), n, None, out.data_ptr(), _stream()))
+        return out
+
+    def match_tile_async(self, mon, ref, mask, window, kconf: KltConf, rows: RowBuffers,
+                         nodata_mon=None, nodata_ref=None):
+        """Enqueue KLT._match_tile for window (x_off, y_off, w, h) of full rasters;
+        no synchronisation (read the counts later with read_stats)."""
+        x_off, y_off, tw, th = window
+        ih, iw = mon.shape
+        _check(self.lib.kr_match_tile(
+            self._h, mon.data_ptr(), _pitch(mon), ref.data_ptr(), _pitch(ref), dtype_code(mon), iw, ih,
+            mask.data_ptr() if mask is not None else None, _pitch(mask) if mask is not None else 0,
+            int(x_off), int(y_off), int(tw), int(th), int(nodata_mon is not None),
+            float(nodata_mon or 0), int(nodata_ref is not None), float(nodata_ref or 0),
+            C.byref(kconf), rows.struct(), _stream()))
+
+    def match_tile(self, mon, ref, mask, window, kconf, rows, nodata_mon=None, nodata_ref=None):
+        """match_tile_async + stats; re-runs once with every candidate when the
+        corner pre-selection was too small.  -> Stats"""
+        for attempt in range(2):
+            self.match_tile_async(mon, ref, mask, window, kconf, rows, nodata_mon, nodata_ref)
+            st = self.read_stats()
+            if not st.select_incomplete or attempt == 1:
+                break
+            self.set_select_all(True)
+        self.set_select_all(False)
+        return st

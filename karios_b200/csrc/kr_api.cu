@@ -1,0 +1,386 @@
+// kr_api.cu -- context, error reporting and the C ABI of include/karios_b200.h.
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+#include <math.h>
+#include <new>
+#include "kr_internal.cuh"
+
+static thread_local char g_err[512] = "";
+
+int kr_set_error(int code, const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+namespace {
+
+__global__ void k_set_u32(uint32_t *p, uint32_t v) { *p = v; }
+
+inline int64_t align_up(int64_t v, int64_t a) { return (v + a - 1) / a * a; }
+
+template <typename T> int dev_alloc(T **p, size_t count)
+{
+    void *q = nullptr;
+    cudaError_t e = cudaMalloc(&q, count * sizeof(T) + 256);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return kr_set_error(KR_ERR_NOMEM, "cudaMalloc of %zu bytes failed: %s", count * sizeof(T),
+                            cudaGetErrorString(e));
+    }
+    *p = (T *)q;
+    return KR_OK;
+}
+
+int elem_size(int dtype)
+{
+    switch (dtype) {
+    case KR_U8: return 1;
+    case KR_U16: case KR_I16: return 2;
+    case KR_F32: return 4;
+    default: return 0;
+    }
+}
+
+int check_conf(const kr_klt_conf *c)
+{
+    if (!c) return kr_set_error(KR_ERR_INVALID, "conf is NULL");
+    if (c->win_size < 3 || c->win_size > 29)
+        return kr_set_error(KR_ERR_UNSUPPORTED, "matching_winsize %d not supported (3..29)", c->win_size);
+    if (c->block_size < 1 || c->block_size > 31)
+        return kr_set_error(KR_ERR_UNSUPPORTED, "blocksize %d not supported (1..31)", c->block_size);
+    return KR_OK;
+}
+
+int check_dims(kr_ctx *ctx, int w, int h)
+{
+    if (!ctx) return kr_set_error(KR_ERR_INVALID, "ctx is NULL");
+    if (w < 1 || h < 1) return kr_set_error(KR_ERR_INVALID, "empty image %dx%d", w, h);
+    if (w > ctx->max_w || h > ctx->max_h)
+        return kr_set_error(KR_ERR_CAPACITY, "image %dx%d larger than the context (%dx%d)", w, h,
+                            ctx->max_w, ctx->max_h);
+    return KR_OK;
+}
+
+// corners (unless given) -> pyramids -> LK round trip -> rows
+int track_common(kr_ctx *ctx, const uint8_t *ref, int64_t ref_pitch, const uint8_t *mon,
+                 int64_t mon_pitch, const uint8_t *mask, int64_t mask_pitch, int w, int h,
+                 const kr_klt_conf *c, const float *p0, int n_p0, int sort_xy, float x_off,
+                 float y_off, kr_rows rows, cudaStream_t s)
+{
+    int n_cap;
+    if (p0) {
+        if (n_p0 < 0 || n_p0 > ctx->corner_cap)
+            return kr_set_error(KR_ERR_CAPACITY, "%d points exceed the context (%lld)", n_p0,
+                                (long long)ctx->corner_cap);
+        if (n_p0 > 0)
+            KR_CUDA(cudaMemcpyAsync(ctx->d_p0, p0, (size_t)n_p0 * 2 * sizeof(float),
+                                    cudaMemcpyDeviceToDevice, s));
+        k_set_u32<<<1, 1, 0, s>>>(&ctx->d_stats->n_corners, (uint32_t)n_p0);
+        KR_LAUNCH_CHECK();
+        n_cap = n_p0;
+    } else {
+        n_cap = (c->max_corners > 0 && c->max_corners < ctx->corner_cap) ? c->max_corners
+                                                                         : (int)ctx->corner_cap;
+        KR_TRY(krl_good_features(ctx, ref, ref_pitch, mask, mask_pitch, w, h, c->max_corners,
+                                 c->quality_level, c->min_distance, c->block_size, c->tail_mode,
+                                 (ctx->force_select_all || c->max_corners <= 0) ? 1 : 0, nullptr, 0,
+                                 ctx->d_p0, n_cap, nullptr, s));
+    }
+    if (rows.capacity < n_cap)
+        return kr_set_error(KR_ERR_CAPACITY, "rows.capacity %d < %d possible rows", rows.capacity, n_cap);
+    KrLkArgs a;
+    memset(&a, 0, sizeof(a));
+    KR_TRY(krl_build_pyramids(ctx, ref, ref_pitch, mon, mon_pitch, w, h, c->win_size, c->max_level, &a, s));
+    a.max_count = c->max_count;
+    a.eps2 = c->eps * c->eps;
+    a.min_eig_thr = (float)c->min_eig_threshold;
+    const float back_thr = (float)c->back_threshold;
+    KR_TRY(krl_lk_roundtrip(a, ctx->d_p0, n_cap, &ctx->d_stats->n_corners, back_thr, ctx->d_p1,
+                            ctx->d_d, ctx->d_keep, s));
+    KR_TRY(krl_emit_rows(ctx, ctx->d_p0, ctx->d_p1, ctx->d_d, ctx->d_keep, n_cap,
+                         &ctx->d_stats->n_corners, sort_xy, back_thr, x_off, y_off, rows, s));
+    return KR_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+KR_API int kr_version(void) { return 100; }
+KR_API const char *kr_last_error(void) { return g_err; }
+
+KR_API int kr_ctx_create(int device, int max_w, int max_h, int max_corners, kr_ctx **out)
+{
+    if (!out) return kr_set_error(KR_ERR_INVALID, "out is NULL");
+    *out = nullptr;
+    if (max_w < 1 || max_h < 1 || max_w > 65535 || max_h > 65535)
+        return kr_set_error(KR_ERR_INVALID, "context size %dx%d out of range (1..65535)", max_w, max_h);
+    KR_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    KR_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10)
+        return kr_set_error(KR_ERR_UNSUPPORTED, "device %d is sm_%d%d; this library is built for sm_100a",
+                            device, prop.major, prop.minor);
+    kr_ctx *c = new (std::nothrow) kr_ctx();
+    if (!c) return kr_set_error(KR_ERR_NOMEM, "host allocation failed");
+    memset(c, 0, sizeof(*c));
+    c->device = device;
+    c->num_sms = prop.multiProcessorCount;
+    c->max_w = max_w; c->max_h = max_h; c->max_corners = max_corners;
+    const int64_t P = (int64_t)max_w * max_h;
+    c->cand_cap = P / 8 > 65536 ? P / 8 : 65536;
+    if (c->cand_cap > P) c->cand_cap = P > 1024 ? P : 1024;
+    c->corner_cap = (max_corners > 0) ? max_corners : c->cand_cap;
+    if (c->corner_cap > c->cand_cap) c->cand_cap = c->corner_cap;
+    c->cell_cap = P / 16 + 1024;
+    c->plane_pitch = align_up(max_w, 128);
+    int rc = KR_OK;
+#define A(expr) if (rc == KR_OK) rc = (expr)
+    A(dev_alloc(&c->d_stats, 1));
+    for (int i = 0; i < 3; i++) A(dev_alloc(&c->d_lut[i], 65536));
+    A(dev_alloc(&c->d_cand, c->cand_cap));
+    A(dev_alloc(&c->d_keys_a, c->cand_cap));
+    A(dev_alloc(&c->d_keys_b, c->cand_cap));
+    A(dev_alloc(&c->d_hist, 4096));
+    A(dev_alloc(&c->d_xy, c->cand_cap));
+    A(dev_alloc(&c->d_state, c->cand_cap));
+    A(dev_alloc(&c->d_next, c->cand_cap));
+    A(dev_alloc(&c->d_cell_head, c->cell_cap));
+    A(dev_alloc(&c->d_mask, c->plane_pitch * max_h));
+    A(dev_alloc(&c->d_lap[0], c->plane_pitch * max_h));
+    A(dev_alloc(&c->d_lap[1], c->plane_pitch * max_h));
+    for (int l = 1; l < KR_MAX_LEVELS; l++) {
+        int64_t lw = ((int64_t)max_w >> l) + 2, lh = ((int64_t)max_h >> l) + 2;
+        c->pyr_pitch[l] = align_up(lw, 128);
+        A(dev_alloc(&c->d_pyr[0][l], c->pyr_pitch[l] * lh));
+        A(dev_alloc(&c->d_pyr[1][l], c->pyr_pitch[l] * lh));
+    }
+    A(dev_alloc(&c->d_p0, c->corner_cap * 2));
+    A(dev_alloc(&c->d_p1, c->corner_cap * 2));
+    A(dev_alloc(&c->d_d, c->corner_cap));
+    A(dev_alloc(&c->d_keep, c->corner_cap));
+#undef A
+    if (rc == KR_OK) {
+        cudaError_t e = cudaMemset(c->d_hist, 0, 4096 * sizeof(uint32_t));
+        if (e == cudaSuccess) e = cudaMemset(c->d_stats, 0, sizeof(KrDevStats));
+        if (e != cudaSuccess) rc = kr_set_error(KR_ERR_CUDA, "cudaMemset: %s", cudaGetErrorString(e));
+    }
+    if (rc == KR_OK) {
+        int bps = 0;
+        rc = kr_nms_occupancy(&bps);
+        if (rc == KR_OK && bps < 1) rc = kr_set_error(KR_ERR_CUDA, "NMS kernel does not fit on an SM");
+        c->nms_grid = c->num_sms * (bps > 2 ? 2 : bps);
+    }
+    if (rc == KR_OK) rc = krl_reset_stats(c, 0);
+    if (rc == KR_OK) {
+        cudaError_t e = cudaDeviceSynchronize();
+        if (e != cudaSuccess) rc = kr_set_error(KR_ERR_CUDA, "context init: %s", cudaGetErrorString(e));
+    }
+    if (rc != KR_OK) {
+        kr_ctx_destroy(c);
+        return rc;
+    }
+    *out = c;
+    return KR_OK;
+}
+
+KR_API void kr_ctx_destroy(kr_ctx *c)
+{
+    if (!c) return;
+    cudaFree(c->d_stats);
+    for (int i = 0; i < 3; i++) cudaFree(c->d_lut[i]);
+    cudaFree(c->d_cand); cudaFree(c->d_keys_a); cudaFree(c->d_keys_b); cudaFree(c->d_hist);
+    cudaFree(c->d_xy); cudaFree(c->d_state); cudaFree(c->d_next); cudaFree(c->d_cell_head);
+    cudaFree(c->d_mask); cudaFree(c->d_lap[0]); cudaFree(c->d_lap[1]);
+    for (int l = 1; l < KR_MAX_LEVELS; l++) { cudaFree(c->d_pyr[0][l]); cudaFree(c->d_pyr[1][l]); }
+    cudaFree(c->d_p0); cudaFree(c->d_p1); cudaFree(c->d_d); cudaFree(c->d_keep);
+    delete c;
+}
+
+KR_API int kr_set_select_all(kr_ctx *ctx, int on)
+{
+    if (!ctx) return kr_set_error(KR_ERR_INVALID, "ctx is NULL");
+    ctx->force_select_all = on ? 1 : 0;
+    return KR_OK;
+}
+
+KR_API int kr_read_stats(kr_ctx *ctx, void *stream, kr_stats *o)
+{
+    if (!ctx || !o) return kr_set_error(KR_ERR_INVALID, "NULL argument");
+    cudaStream_t s = (cudaStream_t)stream;
+    KrDevStats h;
+    KR_CUDA(cudaMemcpyAsync(&h, ctx->d_stats, sizeof(h), cudaMemcpyDeviceToHost, s));
+    KR_CUDA(cudaStreamSynchronize(s));
+    memset(o, 0, sizeof(*o));
+    if (ctx->last_dtype == KR_F32) {
+        o->min_a = kr_f32_dec_bits(h.minf_enc[0], 0); o->max_a = kr_f32_dec_bits(h.maxf_enc[0], 0);
+        o->min_b = kr_f32_dec_bits(h.minf_enc[1], 0); o->max_b = kr_f32_dec_bits(h.maxf_enc[1], 0);
+    } else {
+        o->min_a = h.min_i[0]; o->max_a = h.max_i[0];
+        o->min_b = h.min_i[1]; o->max_b = h.max_i[1];
+    }
+    o->valid = h.valid;
+    o->eig_max = (h.eig_max_enc == KR_ENC_NEG_INF) ? 0.f : kr_f32_dec_bits(h.eig_max_enc, 0);
+    o->n_candidates = h.n_cand;
+    o->n_above_threshold = h.n_thr;
+    o->n_sorted = h.n_sel;
+    o->n_corners = h.n_corners;
+    o->n_kept = h.n_kept;
+    o->nms_rounds = h.nms_rounds;
+    o->overflow = h.overflow;
+    o->select_incomplete = h.select_incomplete;
+    return KR_OK;
+}
+
+KR_API int kr_minmax_mask(kr_ctx *ctx, const void *img_a, int64_t pitch_a, const void *img_b,
+                          int64_t pitch_b, int dtype, int w, int h, int has_nodata_a, double nodata_a,
+                          int has_nodata_b, double nodata_b, uint8_t *mask_out, int64_t mask_pitch,
+                          void *stream)
+{
+    KR_TRY(check_dims(ctx, w, h));
+    if (!img_a) return kr_set_error(KR_ERR_INVALID, "img_a is NULL");
+    if (mask_out && !img_b) return kr_set_error(KR_ERR_INVALID, "the auto mask needs both images");
+    cudaStream_t s = (cudaStream_t)stream;
+    ctx->last_dtype = dtype;
+    KR_TRY(krl_reset_stats(ctx, s));
+    return krl_minmax_mask(ctx, img_a, pitch_a, img_b, pitch_b, dtype, w, h, has_nodata_a, nodata_a,
+                           has_nodata_b, nodata_b, mask_out, mask_pitch, s);
+}
+
+KR_API int kr_u8_laplacian(kr_ctx *ctx, const void *img, int64_t pitch, int dtype, int w, int h,
+                           int slot, int ksize, int invert, uint8_t *out, int64_t out_pitch,
+                           void *stream)
+{
+    KR_TRY(check_dims(ctx, w, h));
+    if (!img || !out) return kr_set_error(KR_ERR_INVALID, "NULL image");
+    cudaStream_t s = (cudaStream_t)stream;
+    if (slot < 0) {
+        slot = 2;
+        if (dtype != KR_U8) KR_TRY(krl_minmax_single(ctx, img, pitch, dtype, w, h, slot, s));
+    } else if (slot > 1) {
+        return kr_set_error(KR_ERR_INVALID, "slot must be -1, 0 or 1");
+    }
+    return krl_laplacian(ctx, img, pitch, dtype, w, h, slot, ksize, invert, out, out_pitch, s);
+}
+
+KR_API int kr_corner_min_eigen_val(kr_ctx *ctx, const uint8_t *img, int64_t pitch, int w, int h,
+                                   int block_size, int tail_mode, float *eig, int64_t eig_pitch,
+                                   void *stream)
+{
+    KR_TRY(check_dims(ctx, w, h));
+    if (!img || !eig) return kr_set_error(KR_ERR_INVALID, "NULL image");
+    return krl_good_features(ctx, img, pitch, nullptr, 0, w, h, 0, 0.0, 0.0, block_size, tail_mode, 0,
+                             eig, eig_pitch, nullptr, 0, nullptr, (cudaStream_t)stream);
+}
+
+KR_API int kr_good_features(kr_ctx *ctx, const uint8_t *img, int64_t pitch, const uint8_t *mask,
+                            int64_t mask_pitch, int w, int h, int max_corners, double quality_level,
+                            double min_distance, int block_size, int tail_mode, float *out_xy,
+                            int capacity, int32_t *d_count, void *stream)
+{
+    KR_TRY(check_dims(ctx, w, h));
+    if (!img || !out_xy || capacity < 1) return kr_set_error(KR_ERR_INVALID, "NULL image / output");
+    int sel_all = ctx->force_select_all || max_corners <= 0;
+    return krl_good_features(ctx, img, pitch, mask, mask_pitch, w, h, max_corners, quality_level,
+                             min_distance, block_size, tail_mode, sel_all, nullptr, 0, out_xy,
+                             capacity, d_count, (cudaStream_t)stream);
+}
+
+KR_API int kr_pyr_down(kr_ctx *ctx, const uint8_t *src, int64_t pitch, int w, int h, uint8_t *dst,
+                       int64_t dst_pitch, void *stream)
+{
+    (void)ctx;
+    if (!src || !dst || w < 1 || h < 1) return kr_set_error(KR_ERR_INVALID, "bad pyrDown arguments");
+    return krl_pyr_down(src, pitch, w, h, dst, dst_pitch, (cudaStream_t)stream);
+}
+
+KR_API int kr_pyr_lk(kr_ctx *ctx, const uint8_t *prev, int64_t prev_pitch, const uint8_t *next,
+                     int64_t next_pitch, int w, int h, const float *p0, int n, const int32_t *d_count,
+                     int win, int max_level, int max_count, double eps, double min_eig_threshold,
+                     float *p1, uint8_t *status, float *err, void *stream)
+{
+    KR_TRY(check_dims(ctx, w, h));
+    if (!prev || !next || !p0 || !p1 || !status || !err)
+        return kr_set_error(KR_ERR_INVALID, "NULL argument");
+    cudaStream_t s = (cudaStream_t)stream;
+    KrLkArgs a;
+    memset(&a, 0, sizeof(a));
+    KR_TRY(krl_build_pyramids(ctx, prev, prev_pitch, next, next_pitch, w, h, win, max_level, &a, s));
+    a.max_count = max_count;
+    a.eps2 = eps * eps;
+    a.min_eig_thr = (float)min_eig_threshold;
+    return krl_lk_single(a, p0, n, d_count, p1, status, err, s);
+}
+
+KR_API int kr_klt_track(kr_ctx *ctx, const uint8_t *ref, int64_t ref_pitch, const uint8_t *mon,
+                        int64_t mon_pitch, const uint8_t *mask, int64_t mask_pitch, int w, int h,
+                        const kr_klt_conf *conf, const float *p0, int n_p0, kr_rows rows, void *stream)
+{
+    KR_TRY(check_dims(ctx, w, h));
+    KR_TRY(check_conf(conf));
+    if (!ref || !mon) return kr_set_error(KR_ERR_INVALID, "NULL image");
+    if (!rows.x0 || !rows.y0 || !rows.dx || !rows.dy || !rows.score || rows.capacity < 1)
+        return kr_set_error(KR_ERR_INVALID, "incomplete rows");
+    return track_common(ctx, ref, ref_pitch, mon, mon_pitch, mask, mask_pitch, w, h, conf, p0, n_p0, 0,
+                        0.f, 0.f, rows, (cudaStream_t)stream);
+}
+
+KR_API int kr_zncc(kr_ctx *ctx, const void *ref, int64_t ref_pitch, int ref_w, int ref_h,
+                   const void *mon, int64_t mon_pitch, int mon_w, int mon_h, int dtype, const float *x0,
+                   const float *y0, const float *dx, const float *dy, int n, const int32_t *d_count,
+                   double *out, void *stream)
+{
+    (void)ctx;
+    if (!ref || !mon || !x0 || !y0 || !dx || !dy || !out)
+        return kr_set_error(KR_ERR_INVALID, "NULL argument");
+    return krl_zncc(ref, ref_pitch, ref_w, ref_h, mon, mon_pitch, mon_w, mon_h, dtype, x0, y0, dx, dy,
+                    nullptr, 0.f, n, (const uint32_t *)d_count, out, (cudaStream_t)stream);
+}
+
+KR_API int kr_match_tile(kr_ctx *ctx, const void *mon, int64_t mon_pitch, const void *ref,
+                         int64_t ref_pitch, int dtype, int img_w, int img_h, const uint8_t *mask,
+                         int64_t mask_pitch, int x_off, int y_off, int tile_w, int tile_h,
+                         int has_nodata_mon, double nodata_mon, int has_nodata_ref, double nodata_ref,
+                         const kr_klt_conf *conf, kr_rows rows, void *stream)
+{
+    KR_TRY(check_dims(ctx, tile_w, tile_h));
+    KR_TRY(check_conf(conf));
+    const int es = elem_size(dtype);
+    if (!es) return kr_set_error(KR_ERR_UNSUPPORTED, "unsupported raster dtype %d", dtype);
+    if (!mon || !ref) return kr_set_error(KR_ERR_INVALID, "NULL image");
+    if (x_off < 0 || y_off < 0 || x_off + tile_w > img_w || y_off + tile_h > img_h)
+        return kr_set_error(KR_ERR_INVALID, "tile window outside the raster");
+    if (!rows.x0 || !rows.y0 || !rows.dx || !rows.dy || !rows.score || rows.capacity < 1)
+        return kr_set_error(KR_ERR_INVALID, "incomplete rows");
+    cudaStream_t s = (cudaStream_t)stream;
+    ctx->last_dtype = dtype;
+    const char *mon_t = (const char *)mon + (int64_t)y_off * mon_pitch + (int64_t)x_off * es;
+    const char *ref_t = (const char *)ref + (int64_t)y_off * ref_pitch + (int64_t)x_off * es;
+    const uint8_t *mask_t = mask ? mask + (int64_t)y_off * mask_pitch + x_off : nullptr;
+
+    KR_TRY(krl_reset_stats(ctx, s));
+    // a = monitored (slot 0), b = reference (slot 1); the auto mask only without a user mask
+    KR_TRY(krl_minmax_mask(ctx, mon_t, mon_pitch, ref_t, ref_pitch, dtype, tile_w, tile_h,
+                           has_nodata_mon, nodata_mon, has_nodata_ref, nodata_ref,
+                           mask ? nullptr : ctx->d_mask, ctx->plane_pitch, s));
+    KR_TRY(krl_laplacian(ctx, mon_t, mon_pitch, dtype, tile_w, tile_h, 0, conf->ksize_mon,
+                         conf->invert_mon, ctx->d_lap[0], ctx->plane_pitch, s));
+    KR_TRY(krl_laplacian(ctx, ref_t, ref_pitch, dtype, tile_w, tile_h, 1, conf->ksize_ref, 0,
+                         ctx->d_lap[1], ctx->plane_pitch, s));
+    const uint8_t *m = mask ? mask_t : ctx->d_mask;
+    const int64_t mp = mask ? mask_pitch : ctx->plane_pitch;
+    KR_TRY(track_common(ctx, ctx->d_lap[1], ctx->plane_pitch, ctx->d_lap[0], ctx->plane_pitch, m, mp,
+                        tile_w, tile_h, conf, nullptr, 0, 1, (float)x_off, (float)y_off, rows, s));
+    if (conf->compute_zncc && rows.zncc)
+        KR_TRY(krl_zncc(ref, ref_pitch, img_w, img_h, mon, mon_pitch, img_w, img_h, dtype, rows.x0,
+                        rows.y0, rows.dx, rows.dy, rows.score, (float)conf->zncc_min_score,
+                        rows.capacity, &ctx->d_stats->n_kept, rows.zncc, s));
+    return KR_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,149 @@
+// kr_internal.cuh -- shared declarations of the sm_100a KLT matching library.
+// Layout of the library:
+//   kr_prep.cu     K1 min/max + auto mask, LUT build, K2 normalise + Laplacian
+//   kr_corners.cu  K3 min-eigenvalue response + candidates, K4 selection (NMS)
+//   kr_sort.cu     chunk bitonic sort + rank merge (u64 keys)
+//   kr_lk.cu       K5 pyrDown, K6 pyramidal LK (forward + backward + back-check)
+//   kr_zncc.cu     K7 ZNCC
+//   kr_api.cu      context, error handling, C ABI (include/karios_b200.h)
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/karios_b200.h"
+
+#define KR_MAX_LEVELS 6
+#define KR_SORT_CHUNK 8192          // keys per bitonic chunk (64 KB of shared memory)
+
+// Device-resident scalars of one context (zeroed / initialised by kr_reset_stats).
+struct KrDevStats {
+    int32_t min_i[3], max_i[3];         // integer rasters: slot 0 = a (mon), 1 = b (ref), 2 = scratch
+    uint32_t minf_enc[3], maxf_enc[3];  // float rasters, order-preserving encoding
+    unsigned long long valid;
+    uint32_t eig_max_enc;               // order-preserving encoding of the masked max
+    uint32_t n_cand, n_thr, n_sel, n_acc, n_corners, n_kept;
+    uint32_t nms_rounds, overflow, select_incomplete;
+    uint32_t thr_bits, cut_bits, hist_shift;
+    uint32_t undecided[3];
+    uint32_t barrier[2];
+    uint32_t n_rowkeys;
+    uint32_t pad[3];
+};
+
+struct kr_ctx {
+    int device, num_sms;
+    int max_w, max_h, max_corners;
+    int64_t cand_cap;       // capacity of the candidate / key lists
+    int64_t corner_cap;     // capacity of corner-sized arrays
+    KrDevStats *d_stats;
+    uint8_t *d_lut[3];      // 65536-entry uint8 tables (slot a, b, scratch)
+    uint64_t *d_cand;       // K3 output: (float bits << 32) | (y*W + x)
+    uint64_t *d_keys_a;     // selected keys / sort ping
+    uint64_t *d_keys_b;     // accepted keys / sort pong
+    uint32_t *d_hist;       // 4096-bin value histogram of the candidates
+    uint32_t *d_xy;         // per selected candidate: x | y << 16
+    uint8_t *d_state;       // NMS state per selected candidate
+    int32_t *d_next;        // NMS cell lists: next pointer per candidate
+    int32_t *d_cell_head;   // NMS cell lists: head per cell
+    int64_t cell_cap;
+    // planes owned by the context (pitch = plane_pitch bytes)
+    int64_t plane_pitch;
+    uint8_t *d_mask;        // auto mask
+    uint8_t *d_lap[2];      // Laplacian planes: 0 = mon, 1 = ref
+    uint8_t *d_pyr[2][KR_MAX_LEVELS];   // pyramid levels >= 1 of (prev, next)
+    int64_t pyr_pitch[KR_MAX_LEVELS];
+    // per-corner scratch
+    float *d_p0, *d_p1;     // corners and forward-tracked points, [corner_cap][2]
+    float *d_d;             // back-check distance
+    uint8_t *d_keep;
+    int nms_grid;           // co-resident grid of the persistent NMS kernel
+    int force_select_all;   // sort every candidate above the threshold (no pre-selection)
+    int last_dtype;         // dtype of the last min/max pass (for kr_read_stats)
+};
+
+// ---- error plumbing (kr_api.cu) ------------------------------------------
+int kr_set_error(int code, const char *fmt, ...);
+#define KR_CUDA(expr)                                                                  \
+    do {                                                                               \
+        cudaError_t _e = (expr);                                                       \
+        if (_e != cudaSuccess)                                                         \
+            return kr_set_error(KR_ERR_CUDA, "%s: %s (%s:%d)", #expr,                  \
+                                cudaGetErrorString(_e), __FILE__, __LINE__);           \
+    } while (0)
+#define KR_LAUNCH_CHECK() KR_CUDA(cudaGetLastError())
+#define KR_TRY(expr)                 \
+    do {                             \
+        int _r = (expr);             \
+        if (_r != KR_OK) return _r;  \
+    } while (0)
+
+// ---- small device helpers ------------------------------------------------
+__host__ __device__ __forceinline__ int kr_reflect101(int p, int len)
+{
+    // cv::borderInterpolate(p, len, BORDER_REFLECT_101)
+    if (len == 1) return 0;
+    while (p < 0 || p >= len) {
+        if (p < 0) p = -p;
+        else p = 2 * (len - 1) - p;
+    }
+    return p;
+}
+
+__device__ __forceinline__ uint32_t kr_f32_enc(float f)
+{
+    uint32_t b = __float_as_uint(f);
+    return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__host__ __device__ __forceinline__ float kr_f32_dec_bits(uint32_t e, int)
+{
+    uint32_t b = (e & 0x80000000u) ? (e & 0x7fffffffu) : ~e;
+#ifdef __CUDA_ARCH__
+    return __uint_as_float(b);
+#else
+    float f;
+    memcpy(&f, &b, 4);
+    return f;
+#endif
+}
+#define KR_ENC_NEG_INF 0x007fffffu   /* kr_f32_enc(-inf) */
+
+// ---- stage launchers (each enqueues on `s`, returns a kr_status) -----------
+int krl_reset_stats(kr_ctx *ctx, cudaStream_t s);
+int krl_minmax_mask(kr_ctx *ctx, const void *a, int64_t pa, const void *b, int64_t pb, int dtype,
+                    int w, int h, int has_nd_a, double nd_a, int has_nd_b, double nd_b,
+                    uint8_t *mask, int64_t pm, cudaStream_t s);
+int krl_minmax_single(kr_ctx *ctx, const void *img, int64_t pitch, int dtype, int w, int h, int slot,
+                      cudaStream_t s);
+int krl_laplacian(kr_ctx *ctx, const void *img, int64_t pitch, int dtype, int w, int h, int slot,
+                  int ksize, int invert, uint8_t *out, int64_t out_pitch, cudaStream_t s);
+int krl_good_features(kr_ctx *ctx, const uint8_t *img, int64_t pitch, const uint8_t *mask,
+                      int64_t mask_pitch, int w, int h, int max_corners, double quality,
+                      double min_distance, int block, int tail_mode, int select_all, float *eig_out,
+                      int64_t eig_pitch, float *out_xy, int capacity, int32_t *d_count,
+                      cudaStream_t s);
+int kr_nms_occupancy(int *blocks_per_sm);
+int krl_sort_u64(kr_ctx *ctx, uint64_t *keys, uint64_t *out, const uint32_t *d_n, int64_t cap,
+                 int descending, cudaStream_t s);
+int krl_pyr_down(const uint8_t *src, int64_t pitch, int w, int h, uint8_t *dst, int64_t dst_pitch,
+                 cudaStream_t s);
+struct KrLkArgs {
+    const uint8_t *img[2][KR_MAX_LEVELS];   // [0] = prev pyramid, [1] = next pyramid
+    int64_t pitch[2][KR_MAX_LEVELS];
+    int w[KR_MAX_LEVELS], h[KR_MAX_LEVELS];
+    int levels;                             // top level index (0 = no pyramid)
+    int win, max_count;
+    double eps2;
+    float min_eig_thr;
+};
+int krl_build_pyramids(kr_ctx *ctx, const uint8_t *prev, int64_t pp, const uint8_t *next, int64_t np_,
+                       int w, int h, int win, int max_level, KrLkArgs *args, cudaStream_t s);
+int krl_lk_single(const KrLkArgs &a, const float *p0, int n, const int32_t *d_count, float *p1,
+                  uint8_t *status, float *err, cudaStream_t s);
+int krl_lk_roundtrip(const KrLkArgs &a, const float *p0, int n_cap, const uint32_t *d_count,
+                     float back_thr, float *p1, float *dist, uint8_t *keep, cudaStream_t s);
+int krl_emit_rows(kr_ctx *ctx, const float *p0, const float *p1, const float *dist,
+                  const uint8_t *keep, int n_cap, const uint32_t *d_count, int sort_xy,
+                  float back_thr, float x_off, float y_off, kr_rows rows, cudaStream_t s);
+int krl_zncc(const void *ref, int64_t rp, int rw, int rh, const void *mon, int64_t mp, int mw, int mh,
+             int dtype, const float *x0, const float *y0, const float *dx, const float *dy,
+             const float *score, float min_score, int n, const uint32_t *d_count, double *out,
+             cudaStream_t s);

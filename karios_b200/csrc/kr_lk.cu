@@ -1,0 +1,471 @@
+// kr_lk.cu -- K5 (pyrDown) and K6 (pyramidal Lucas-Kanade, forward + backward +
+// back-check), plus the compaction of the surviving rows.
+//
+// Replaces cv2.calcOpticalFlowPyrLK(prev, next, p0, None, winSize=(w,w),
+// maxLevel=1, criteria=(EPS|COUNT, 30, 0.03)) called twice at
+// karios/matcher/klt.py:134-140 and the back-check of klt.py:142-159.
+// Semantics follow SURVEY.md A.5 (verified against cv2 4.13 by
+// oracle/klt_oracle.c: status identical, positions within ~1e-4 px):
+//   pyramid level l+1 = 5-tap [1,4,6,4,1] pyrDown, (sum+128)>>8, REFLECT_101;
+//   Scharr derivatives of the previous image (zero outside the image);
+//   14-bit fixed-point bilinear weights, patch values with 5 fractional bits;
+//   normal equations from exact integer sums (OpenCV: float32 SIMD sums);
+//   termination |delta|^2 <= eps^2 or the 0.01 oscillation test.
+//
+// One warp tracks one point.  Lane l owns window column l: a window row is one
+// coalesced byte load per lane, horizontal neighbours come from warp shuffles,
+// vertical neighbours from the previous row kept in registers.  The template
+// patch (Iw, Ix, Iy) lives in shared memory (6 B per window pixel); the 2x2
+// system is reduced with integer warp shuffles.
+#include <math.h>
+#include <float.h>
+#include "kr_internal.cuh"
+
+namespace {
+
+// ---------------------------------------------------------------- K5 pyrDown
+constexpr int PD_TW = 64, PD_TH = 16, PD_THREADS = 256;
+constexpr int PD_IW = 2 * PD_TW + 3, PD_IH = 2 * PD_TH + 3;
+
+struct PyrPair {
+    const uint8_t *src[2];
+    uint8_t *dst[2];
+    int64_t src_pitch[2], dst_pitch[2];
+};
+
+__global__ void __launch_bounds__(PD_THREADS) k_pyr_down(PyrPair pp, int w, int h)
+{
+    __shared__ uint8_t pix[PD_IH][PD_IW + 1];
+    __shared__ uint16_t hs[PD_IH][PD_TW];
+    const uint8_t *__restrict__ src = pp.src[blockIdx.z];
+    uint8_t *__restrict__ dst = pp.dst[blockIdx.z];
+    const int64_t sp = pp.src_pitch[blockIdx.z], dp = pp.dst_pitch[blockIdx.z];
+    const int dw = (w + 1) >> 1, dh = (h + 1) >> 1;
+    const int ox = blockIdx.x * PD_TW, oy = blockIdx.y * PD_TH;
+    const int ix0 = 2 * ox - 2, iy0 = 2 * oy - 2;
+    for (int i = threadIdx.x; i < PD_IH * PD_IW; i += PD_THREADS) {
+        int ty = i / PD_IW, tx = i - ty * PD_IW;
+        int gy = kr_reflect101(iy0 + ty, h), gx = kr_reflect101(ix0 + tx, w);
+        pix[ty][tx] = __ldg(src + (int64_t)gy * sp + gx);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < PD_IH * PD_TW; i += PD_THREADS) {
+        int ty = i / PD_TW, tx = i - ty * PD_TW;
+        const uint8_t *p = &pix[ty][2 * tx];
+        hs[ty][tx] = (uint16_t)(p[0] + p[4] + 4 * (p[1] + p[3]) + 6 * p[2]);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < PD_TH * PD_TW; i += PD_THREADS) {
+        int ty = i / PD_TW, tx = i - ty * PD_TW;
+        int gx = ox + tx, gy = oy + ty;
+        if (gx >= dw || gy >= dh) continue;
+        int r = 2 * ty;
+        int acc = hs[r][tx] + hs[r + 4][tx] + 4 * (hs[r + 1][tx] + hs[r + 3][tx]) + 6 * hs[r + 2][tx];
+        dst[(int64_t)gy * dp + gx] = (uint8_t)((acc + 128) >> 8);
+    }
+}
+
+// --------------------------------------------------------------------- K6 LK
+constexpr int LK_WARPS = 8;
+constexpr int W_BITS = 14;
+
+__device__ __forceinline__ long long warp_sum_ll(long long v)
+{
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+__device__ __forceinline__ void lk_weights(float a, float b, int &w00, int &w01, int &w10, int &w11)
+{
+    const float one_a = __fsub_rn(1.f, a), one_b = __fsub_rn(1.f, b);
+    const float sc = (float)(1 << W_BITS);
+    w00 = __float2int_rn(__fmul_rn(__fmul_rn(one_a, one_b), sc));
+    w01 = __float2int_rn(__fmul_rn(__fmul_rn(a, one_b), sc));
+    w10 = __float2int_rn(__fmul_rn(__fmul_rn(one_a, b), sc));
+    w11 = (1 << W_BITS) - w00 - w01 - w10;
+}
+
+// Sum over the window of |J(pos) - Iw| (flag ABS) or of diff*Ix, diff*Iy, at
+// integer origin (inx, iny) with the given bilinear weights.  All lanes get
+// the totals.
+template <bool ABS>
+__device__ __forceinline__ void lk_residual(const uint8_t *__restrict__ J, int64_t pJ, int w, int h,
+                                            int inx, int iny, int win, int w00, int w01, int w10,
+                                            int w11, const int16_t *sIw, const int32_t *sIxy,
+                                            int lane, long long &o1, long long &o2)
+{
+    const int col = kr_reflect101(inx + min(lane, win), w);
+    const bool act = lane < win;
+    int b1 = 0, b2 = 0;
+    int tv = 0, tvr = 0;
+    for (int r = 0; r <= win; r++) {
+        const uint8_t *rowp = J + (int64_t)kr_reflect101(iny + r, h) * pJ;
+        int v = __ldg(rowp + col);
+        int vr = __shfl_down_sync(0xffffffffu, v, 1);
+        if (r >= 1) {
+            int val = (tv * w00 + tvr * w01 + v * w10 + vr * w11 + (1 << (W_BITS - 5 - 1))) >> (W_BITS - 5);
+            if (act) {
+                int o = (r - 1) * win + lane;
+                int diff = val - (int)sIw[o];
+                if (ABS) {
+                    b1 += abs(diff);
+                } else {
+                    int32_t pk = sIxy[o];
+                    b1 += diff * (int)(int16_t)(pk & 0xffff);
+                    b2 += diff * (pk >> 16);
+                }
+            }
+        }
+        tv = v;
+        tvr = vr;
+    }
+    o1 = warp_sum_ll((long long)b1);
+    o2 = ABS ? 0ll : warp_sum_ll((long long)b2);
+}
+
+// calcOpticalFlowPyrLK for one point, all levels, direction dir (0: img[0] is
+// the previous image, 1: img[1] is).  Uniform across the warp.
+__device__ void lk_track(const KrLkArgs &A, int dir, float ptx, float pty, float &ox, float &oy,
+                         uint8_t &status, float &err, int16_t *sIw, int32_t *sIxy, int lane)
+{
+    const int win = A.win;
+    const float half = __fmul_rn((float)(win - 1), 0.5f);
+    const float FLT_SCALE = 1.f / (float)(1 << 20);
+    status = 1;
+    err = 0.f;
+    ox = 0.f;
+    oy = 0.f;
+    for (int l = A.levels; l >= 0; l--) {
+        const uint8_t *__restrict__ I = A.img[dir][l];
+        const uint8_t *__restrict__ J = A.img[dir ^ 1][l];
+        const int64_t pI = A.pitch[dir][l], pJ = A.pitch[dir ^ 1][l];
+        const int w = A.w[l], h = A.h[l];
+        const float scale = (float)(1.0 / (double)(1 << l));
+        float px = __fmul_rn(ptx, scale), py = __fmul_rn(pty, scale);
+        float nx, ny;
+        if (l == A.levels) { nx = px; ny = py; }
+        else { nx = __fmul_rn(ox, 2.f); ny = __fmul_rn(oy, 2.f); }
+        ox = nx; oy = ny;
+        px = __fsub_rn(px, half); py = __fsub_rn(py, half);
+        const int ipx = (int)floorf(px), ipy = (int)floorf(py);
+        if (ipx < -win || ipx >= w || ipy < -win || ipy >= h) {
+            if (l == 0) { status = 0; err = 0.f; }
+            continue;
+        }
+        int w00, w01, w10, w11;
+        lk_weights(__fsub_rn(px, (float)ipx), __fsub_rn(py, (float)ipy), w00, w01, w10, w11);
+
+        // ---- template patch: lane <-> image column ipx - 1 + lane ----------
+        {
+            const int cx = ipx - 1 + min(lane, win + 2);
+            const int col = kr_reflect101(cx, w);
+            const bool col_in = cx >= 0 && cx < w;
+            const bool act = lane >= 1 && lane <= win;
+            int a = 0, b = 0, c = 0;
+            int t_dx = 0, t_dxr = 0, t_dy = 0, t_dyr = 0, t_pv = 0, t_pvr = 0;
+            int s11 = 0, s12 = 0, s22 = 0;
+            __syncwarp();
+            for (int r = 0; r < win + 3; r++) {
+                const int ry = ipy - 1 + r;
+                a = b; b = c;
+                c = __ldg(I + (int64_t)kr_reflect101(ry, h) * pI + col);
+                if (r < 2) continue;
+                const int Y = ry - 1;                   // row of the derivative being formed
+                int S = 3 * (a + c) + 10 * b, D = c - a;
+                int Sl = __shfl_up_sync(0xffffffffu, S, 1), Sr = __shfl_down_sync(0xffffffffu, S, 1);
+                int Dl = __shfl_up_sync(0xffffffffu, D, 1), Dr = __shfl_down_sync(0xffffffffu, D, 1);
+                int dxv = Sr - Sl, dyv = 3 * (Dl + Dr) + 10 * D;
+                if (!(col_in && Y >= 0 && Y < h)) { dxv = 0; dyv = 0; }    // derivative border = 0
+                int pv = b;
+                int dxr = __shfl_down_sync(0xffffffffu, dxv, 1);
+                int dyr = __shfl_down_sync(0xffffffffu, dyv, 1);
+                int pvr = __shfl_down_sync(0xffffffffu, pv, 1);
+                if (r >= 3 && act) {
+                    int y = r - 3;
+                    int ix = (t_dx * w00 + t_dxr * w01 + dxv * w10 + dxr * w11 + (1 << (W_BITS - 1))) >> W_BITS;
+                    int iy = (t_dy * w00 + t_dyr * w01 + dyv * w10 + dyr * w11 + (1 << (W_BITS - 1))) >> W_BITS;
+                    int iv = (t_pv * w00 + t_pvr * w01 + pv * w10 + pvr * w11 + (1 << (W_BITS - 5 - 1))) >> (W_BITS - 5);
+                    int o = y * win + (lane - 1);
+                    sIw[o] = (int16_t)iv;
+                    sIxy[o] = (int32_t)((uint32_t)(ix & 0xffff) | ((uint32_t)iy << 16));
+                    s11 += ix * ix; s12 += ix * iy; s22 += iy * iy;
+                }
+                t_dx = dxv; t_dxr = dxr; t_dy = dyv; t_dyr = dyr; t_pv = pv; t_pvr = pvr;
+            }
+            __syncwarp();
+            const long long S11 = warp_sum_ll((long long)s11), S12 = warp_sum_ll((long long)s12),
+                            S22 = warp_sum_ll((long long)s22);
+            const float A11 = __fmul_rn((float)S11, FLT_SCALE), A12 = __fmul_rn((float)S12, FLT_SCALE),
+                        A22 = __fmul_rn((float)S22, FLT_SCALE);
+            float Dt = __fsub_rn(__fmul_rn(A11, A22), __fmul_rn(A12, A12));
+            const float dd = __fsub_rn(A11, A22);
+            const float rad = __fadd_rn(__fmul_rn(dd, dd), __fmul_rn(__fmul_rn(4.f, A12), A12));
+            const float min_eig = __fdiv_rn(__fsub_rn(__fadd_rn(A22, A11), __fsqrt_rn(rad)),
+                                            (float)(2 * win * win));
+            if (min_eig < A.min_eig_thr || Dt < FLT_EPSILON) {
+                if (l == 0) status = 0;
+                continue;
+            }
+            Dt = __fdiv_rn(1.f, Dt);
+
+            // ---- iterations on J ------------------------------------------
+            nx = __fsub_rn(nx, half); ny = __fsub_rn(ny, half);
+            float pdx = 0.f, pdy = 0.f;
+            for (int j = 0; j < A.max_count; j++) {
+                const int inx = (int)floorf(nx), iny = (int)floorf(ny);
+                if (inx < -win || inx >= w || iny < -win || iny >= h) {
+                    if (l == 0) status = 0;
+                    break;
+                }
+                lk_weights(__fsub_rn(nx, (float)inx), __fsub_rn(ny, (float)iny), w00, w01, w10, w11);
+                long long sb1, sb2;
+                lk_residual<false>(J, pJ, w, h, inx, iny, win, w00, w01, w10, w11, sIw, sIxy, lane, sb1, sb2);
+                const float b1 = __fmul_rn((float)sb1, FLT_SCALE), b2 = __fmul_rn((float)sb2, FLT_SCALE);
+                const float ddx = __fmul_rn(__fsub_rn(__fmul_rn(A12, b2), __fmul_rn(A22, b1)), Dt);
+                const float ddy = __fmul_rn(__fsub_rn(__fmul_rn(A12, b1), __fmul_rn(A11, b2)), Dt);
+                nx = __fadd_rn(nx, ddx); ny = __fadd_rn(ny, ddy);
+                ox = __fadd_rn(nx, half); oy = __fadd_rn(ny, half);
+                if ((double)ddx * (double)ddx + (double)ddy * (double)ddy <= A.eps2) break;
+                if (j > 0 && fabs((double)__fadd_rn(ddx, pdx)) < 0.01 &&
+                    fabs((double)__fadd_rn(ddy, pdy)) < 0.01) {
+                    ox = __fsub_rn(ox, __fmul_rn(ddx, 0.5f));
+                    oy = __fsub_rn(oy, __fmul_rn(ddy, 0.5f));
+                    break;
+                }
+                pdx = ddx; pdy = ddy;
+            }
+            if (status && l == 0) {
+                const float ex = __fsub_rn(ox, half), ey = __fsub_rn(oy, half);
+                const int iex = (int)floorf(ex), iey = (int)floorf(ey);
+                if (iex < -win || iex >= w || iey < -win || iey >= h) {
+                    status = 0;
+                } else {
+                    lk_weights(__fsub_rn(ex, (float)iex), __fsub_rn(ey, (float)iey), w00, w01, w10, w11);
+                    long long sabs, dummy;
+                    lk_residual<true>(J, pJ, w, h, iex, iey, win, w00, w01, w10, w11, sIw, sIxy, lane, sabs, dummy);
+                    err = __fdiv_rn(__fmul_rn((float)sabs, 1.f), (float)(32 * win * win));
+                }
+            }
+        }
+    }
+}
+
+__device__ __forceinline__ int lk_count(int n, const int32_t *d_count)
+{
+    if (d_count) { int c = *d_count; return c < n ? c : n; }
+    return n;
+}
+
+__global__ void __launch_bounds__(LK_WARPS * 32)
+k_lk_single(KrLkArgs A, const float *__restrict__ p0, int n, const int32_t *d_count,
+            float *__restrict__ p1, uint8_t *__restrict__ status, float *__restrict__ err)
+{
+    extern __shared__ __align__(16) unsigned char lk_smem[];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int ww = A.win * A.win;
+    int32_t *sIxy = reinterpret_cast<int32_t *>(lk_smem) + wid * ww;
+    int16_t *sIw = reinterpret_cast<int16_t *>(reinterpret_cast<int32_t *>(lk_smem) + LK_WARPS * ww) + wid * ww;
+    const int cnt = lk_count(n, d_count);
+    for (int i = blockIdx.x * LK_WARPS + wid; i < cnt; i += gridDim.x * LK_WARPS) {
+        float ox, oy, e;
+        uint8_t st;
+        lk_track(A, 0, p0[2 * i], p0[2 * i + 1], ox, oy, st, e, sIw, sIxy, lane);
+        if (lane == 0) {
+            p1[2 * i] = ox; p1[2 * i + 1] = oy;
+            status[i] = st;
+            err[i] = e;
+        }
+    }
+}
+
+// forward (ref -> mon), backward (mon -> ref) from the forward result, then the
+// back-check of klt.py:142-144: d = max|p0 - p0r|, keep = d < 0.1 (float32).
+__global__ void __launch_bounds__(LK_WARPS * 32)
+k_lk_roundtrip(KrLkArgs A, const float *__restrict__ p0, int n_cap, const uint32_t *d_count,
+               float back_thr, float *__restrict__ p1, float *__restrict__ dist,
+               uint8_t *__restrict__ keep)
+{
+    extern __shared__ __align__(16) unsigned char lk_smem[];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int ww = A.win * A.win;
+    int32_t *sIxy = reinterpret_cast<int32_t *>(lk_smem) + wid * ww;
+    int16_t *sIw = reinterpret_cast<int16_t *>(reinterpret_cast<int32_t *>(lk_smem) + LK_WARPS * ww) + wid * ww;
+    int cnt = (int)min(*d_count, (uint32_t)n_cap);
+    for (int i = blockIdx.x * LK_WARPS + wid; i < cnt; i += gridDim.x * LK_WARPS) {
+        const float x0 = p0[2 * i], y0 = p0[2 * i + 1];
+        float x1, y1, xr, yr, e;
+        uint8_t st;
+        lk_track(A, 0, x0, y0, x1, y1, st, e, sIw, sIxy, lane);
+        lk_track(A, 1, x1, y1, xr, yr, st, e, sIw, sIxy, lane);
+        if (lane == 0) {
+            float d = fmaxf(fabsf(__fsub_rn(x0, xr)), fabsf(__fsub_rn(y0, yr)));
+            p1[2 * i] = x1; p1[2 * i + 1] = y1;
+            dist[i] = d;
+            keep[i] = (d < back_thr) ? 1 : 0;
+        }
+    }
+}
+
+// ------------------------------------------------------------ rows (a9, a11)
+__global__ void __launch_bounds__(256)
+k_row_keys(const float *__restrict__ p0, const uint8_t *__restrict__ keep, int n_cap,
+           const uint32_t *d_count, int sort_xy, uint64_t *__restrict__ keys, KrDevStats *st)
+{
+    __shared__ uint32_t s_cnt[8];
+    __shared__ uint32_t s_base;
+    const uint32_t n = min(*d_count, (uint32_t)n_cap);
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    for (uint32_t i0 = blockIdx.x * blockDim.x; i0 < n; i0 += gridDim.x * blockDim.x) {
+        uint32_t i = i0 + threadIdx.x;
+        bool k = (i < n) && keep[i];
+        unsigned bal = __ballot_sync(0xffffffffu, k);
+        if (lane == 0) s_cnt[wid] = __popc(bal);
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            uint32_t tot = 0;
+            for (int q = 0; q < 8; q++) { uint32_t c = s_cnt[q]; s_cnt[q] = tot; tot += c; }
+            s_base = tot ? atomicAdd(&st->n_rowkeys, tot) : 0;
+        }
+        __syncthreads();
+        if (k) {
+            uint64_t hi = 0;
+            if (sort_xy) hi = ((uint64_t)(uint32_t)p0[2 * i] << 16) | (uint64_t)(uint32_t)p0[2 * i + 1];
+            keys[s_base + s_cnt[wid] + __popc(bal & ((1u << lane) - 1))] = (hi << 32) | i;
+        }
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(256)
+k_gather_rows(const uint64_t *__restrict__ sorted, const float *__restrict__ p0,
+              const float *__restrict__ p1, const float *__restrict__ dist, float back_thr,
+              float x_off, float y_off, kr_rows rows, KrDevStats *st)
+{
+    uint32_t n = st->n_rowkeys;
+    if (n > (uint32_t)rows.capacity) n = (uint32_t)rows.capacity;
+    for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < n; r += gridDim.x * blockDim.x) {
+        uint32_t i = (uint32_t)sorted[r];
+        float x0 = p0[2 * i], y0 = p0[2 * i + 1];
+        rows.x0[r] = __fadd_rn(x0, x_off);
+        rows.y0[r] = __fadd_rn(y0, y_off);
+        rows.dx[r] = __fsub_rn(p1[2 * i], x0);
+        rows.dy[r] = __fsub_rn(p1[2 * i + 1], y0);
+        rows.score[r] = __fsub_rn(1.f, __fdiv_rn(dist[i], back_thr));
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) st->n_kept = n;
+}
+
+__global__ void k_clear_rowkeys(KrDevStats *st) { st->n_rowkeys = 0; st->n_kept = 0; }
+
+size_t lk_smem_bytes(int win) { return (size_t)LK_WARPS * win * win * 6; }
+
+int lk_prepare(const KrLkArgs &a, size_t *smem)
+{
+    if (a.win < 3 || a.win > 29)
+        return kr_set_error(KR_ERR_UNSUPPORTED, "LK window %d not supported (3..29)", a.win);
+    *smem = lk_smem_bytes(a.win);
+    static size_t set1 = 0;
+    if (*smem > set1 && *smem > 48 * 1024) {
+        KR_CUDA(cudaFuncSetAttribute(k_lk_single, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)*smem));
+        KR_CUDA(cudaFuncSetAttribute(k_lk_roundtrip, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)*smem));
+        set1 = *smem;
+    }
+    return KR_OK;
+}
+
+}  // namespace
+
+int krl_pyr_down(const uint8_t *src, int64_t pitch, int w, int h, uint8_t *dst, int64_t dst_pitch,
+                 cudaStream_t s)
+{
+    PyrPair pp;
+    pp.src[0] = pp.src[1] = src; pp.dst[0] = pp.dst[1] = dst;
+    pp.src_pitch[0] = pp.src_pitch[1] = pitch; pp.dst_pitch[0] = pp.dst_pitch[1] = dst_pitch;
+    int dw = (w + 1) / 2, dh = (h + 1) / 2;
+    dim3 grid((dw + PD_TW - 1) / PD_TW, (dh + PD_TH - 1) / PD_TH, 1);
+    k_pyr_down<<<grid, PD_THREADS, 0, s>>>(pp, w, h);
+    KR_LAUNCH_CHECK();
+    return KR_OK;
+}
+
+// buildOpticalFlowPyramid: a level is added while both halved sizes exceed the window.
+int krl_build_pyramids(kr_ctx *ctx, const uint8_t *prev, int64_t pp, const uint8_t *next, int64_t np_,
+                       int w, int h, int win, int max_level, KrLkArgs *a, cudaStream_t s)
+{
+    if (max_level >= KR_MAX_LEVELS) max_level = KR_MAX_LEVELS - 1;
+    if (max_level < 0) max_level = 0;
+    if ((int64_t)w * h > (int64_t)ctx->max_w * ctx->max_h || w > 65535 || h > 65535)
+        return kr_set_error(KR_ERR_CAPACITY, "image %dx%d larger than the context (%dx%d)", w, h,
+                            ctx->max_w, ctx->max_h);
+    a->img[0][0] = prev; a->img[1][0] = next;
+    a->pitch[0][0] = pp; a->pitch[1][0] = np_;
+    a->w[0] = w; a->h[0] = h;
+    a->win = win;
+    int levels = 0;
+    for (int l = 0; l < max_level; l++) {
+        int nw = (a->w[l] + 1) / 2, nh = (a->h[l] + 1) / 2;
+        if (nw <= win || nh <= win) break;
+        // planes of one level are packed with a 128-byte aligned pitch
+        int64_t pitch = ((int64_t)nw + 127) & ~(int64_t)127;
+        a->w[l + 1] = nw; a->h[l + 1] = nh;
+        a->img[0][l + 1] = ctx->d_pyr[0][l + 1]; a->img[1][l + 1] = ctx->d_pyr[1][l + 1];
+        a->pitch[0][l + 1] = a->pitch[1][l + 1] = pitch;
+        PyrPair q;
+        q.src[0] = a->img[0][l]; q.src[1] = a->img[1][l];
+        q.dst[0] = ctx->d_pyr[0][l + 1]; q.dst[1] = ctx->d_pyr[1][l + 1];
+        q.src_pitch[0] = a->pitch[0][l]; q.src_pitch[1] = a->pitch[1][l];
+        q.dst_pitch[0] = q.dst_pitch[1] = pitch;
+        dim3 grid((nw + PD_TW - 1) / PD_TW, (nh + PD_TH - 1) / PD_TH, 2);
+        k_pyr_down<<<grid, PD_THREADS, 0, s>>>(q, a->w[l], a->h[l]);
+        KR_LAUNCH_CHECK();
+        levels = l + 1;
+    }
+    a->levels = levels;
+    return KR_OK;
+}
+
+int krl_lk_single(const KrLkArgs &a, const float *p0, int n, const int32_t *d_count, float *p1,
+                  uint8_t *status, float *err, cudaStream_t s)
+{
+    size_t smem;
+    KR_TRY(lk_prepare(a, &smem));
+    if (n <= 0) return KR_OK;
+    int grid = (n + LK_WARPS - 1) / LK_WARPS;
+    k_lk_single<<<grid, LK_WARPS * 32, smem, s>>>(a, p0, n, d_count, p1, status, err);
+    KR_LAUNCH_CHECK();
+    return KR_OK;
+}
+
+int krl_lk_roundtrip(const KrLkArgs &a, const float *p0, int n_cap, const uint32_t *d_count,
+                     float back_thr, float *p1, float *dist, uint8_t *keep, cudaStream_t s)
+{
+    size_t smem;
+    KR_TRY(lk_prepare(a, &smem));
+    if (n_cap <= 0) return KR_OK;
+    int grid = (n_cap + LK_WARPS - 1) / LK_WARPS;
+    if (grid > 65535 * 8) grid = 65535 * 8;
+    k_lk_roundtrip<<<grid, LK_WARPS * 32, smem, s>>>(a, p0, n_cap, d_count, back_thr, p1, dist, keep);
+    KR_LAUNCH_CHECK();
+    return KR_OK;
+}
+
+int krl_emit_rows(kr_ctx *ctx, const float *p0, const float *p1, const float *dist,
+                  const uint8_t *keep, int n_cap, const uint32_t *d_count, int sort_xy,
+                  float back_thr, float x_off, float y_off, kr_rows rows, cudaStream_t s)
+{
+    k_clear_rowkeys<<<1, 1, 0, s>>>(ctx->d_stats);
+    KR_LAUNCH_CHECK();
+    int grid = (n_cap + 255) / 256;
+    if (grid > ctx->num_sms * 8) grid = ctx->num_sms * 8;
+    if (grid < 1) grid = 1;
+    k_row_keys<<<grid, 256, 0, s>>>(p0, keep, n_cap, d_count, sort_xy, ctx->d_keys_b, ctx->d_stats);
+    KR_LAUNCH_CHECK();
+    // ascending (x0, y0, index): DataFrame.sort_values(["x0", "y0"]) (klt.py:348),
+    // or plain index order (sort_xy == 0) = boolean-mask filtering (klt.py:150-153)
+    KR_TRY(krl_sort_u64(ctx, ctx->d_keys_b, ctx->d_keys_a, &ctx->d_stats->n_rowkeys,
+                        (int64_t)n_cap, 0, s));
+    k_gather_rows<<<grid, 256, 0, s>>>(ctx->d_keys_a, p0, p1, dist, back_thr, x_off, y_off, rows,
+                                       ctx->d_stats);
+    KR_LAUNCH_CHECK();
+    return KR_OK;
+}

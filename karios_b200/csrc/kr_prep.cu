@@ -1,0 +1,400 @@
+// kr_prep.cu -- K1 (min/max + auto mask + valid count), LUT build and K2
+// (uint8 normalisation fused with the integer Laplacian).
+//
+// Reference call sites replaced:
+//   karios/matcher/klt.py:42-49    _to_uint8 (np.nanmin/np.nanmax, float64 scale, truncation)
+//   karios/matcher/klt.py:268-276  auto mask + valid pixel count
+//   karios/matcher/klt.py:419      255 - uint8(mon)  (polarity)
+//   karios/matcher/klt.py:433-434  cv2.Laplacian(u8, cv2.CV_8U, ksize)
+#include <float.h>
+#include <limits.h>
+#include "kr_internal.cuh"
+
+namespace {
+
+template <typename T> struct PixTraits;
+template <> struct PixTraits<uint8_t> { typedef int acc_t; static constexpr bool is_float = false; };
+template <> struct PixTraits<uint16_t> { typedef int acc_t; static constexpr bool is_float = false; };
+template <> struct PixTraits<int16_t> { typedef int acc_t; static constexpr bool is_float = false; };
+template <> struct PixTraits<float> { typedef float acc_t; static constexpr bool is_float = true; };
+
+template <typename T> struct alignas(sizeof(T) * 4) Vec4 { T v[4]; };
+
+__device__ __forceinline__ int acc_min(int a, int b) { return min(a, b); }
+__device__ __forceinline__ int acc_max(int a, int b) { return max(a, b); }
+__device__ __forceinline__ float acc_min(float a, float b) { return fminf(a, b); }   // NaN-ignoring
+__device__ __forceinline__ float acc_max(float a, float b) { return fmaxf(a, b); }
+
+template <typename A> __device__ __forceinline__ A warp_min(A v)
+{
+    for (int o = 16; o > 0; o >>= 1) v = acc_min(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+template <typename A> __device__ __forceinline__ A warp_max(A v)
+{
+    for (int o = 16; o > 0; o >>= 1) v = acc_max(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+__device__ __forceinline__ void publish_minmax(KrDevStats *st, int slot, int mn, int mx)
+{
+    atomicMin(&st->min_i[slot], mn);
+    atomicMax(&st->max_i[slot], mx);
+}
+__device__ __forceinline__ void publish_minmax(KrDevStats *st, int slot, float mn, float mx)
+{
+    // +inf / -inf are the identities when no finite value was seen by this block
+    atomicMin(&st->minf_enc[slot], kr_f32_enc(mn));
+    atomicMax(&st->maxf_enc[slot], kr_f32_enc(mx));
+}
+
+// K1.  One block walks rows blockIdx.x, blockIdx.x + gridDim.x, ...; threads
+// stride the row with 4-pixel vector loads when every row is suitably aligned.
+template <typename T, bool VEC>
+__global__ void __launch_bounds__(256)
+k_minmax_mask(const T *__restrict__ a, int64_t pa, const T *__restrict__ b, int64_t pb, int w, int h,
+              int slot_a, int slot_b, int has_nd_a, double nd_a, int has_nd_b, double nd_b,
+              uint8_t *__restrict__ mask, int64_t pm, KrDevStats *st)
+{
+    typedef typename PixTraits<T>::acc_t A;
+    const bool isf = PixTraits<T>::is_float;
+    A mn_a = isf ? (A)INFINITY : (A)INT_MAX, mx_a = isf ? (A)-INFINITY : (A)INT_MIN;
+    A mn_b = mn_a, mx_b = mx_a;
+    unsigned cnt = 0;
+
+    auto one = [&](T va, T vb, bool have_b) -> uint8_t {
+        A xa = (A)va;
+        mn_a = acc_min(mn_a, xa);
+        mx_a = acc_max(mx_a, xa);
+        bool ok = va != (T)0;
+        if (isf) ok = ok && isfinite((float)va);
+        if (has_nd_a) ok = ok && ((double)va != nd_a);
+        if (have_b) {
+            A xb = (A)vb;
+            mn_b = acc_min(mn_b, xb);
+            mx_b = acc_max(mx_b, xb);
+            ok = ok && vb != (T)0;
+            if (isf) ok = ok && isfinite((float)vb);
+            if (has_nd_b) ok = ok && ((double)vb != nd_b);
+        }
+        return ok ? 1 : 0;
+    };
+
+    const bool have_b = b != nullptr;
+    for (int y = blockIdx.x; y < h; y += gridDim.x) {
+        const T *ra = (const T *)((const char *)a + (int64_t)y * pa);
+        const T *rb = have_b ? (const T *)((const char *)b + (int64_t)y * pb) : nullptr;
+        uint8_t *rm = mask ? mask + (int64_t)y * pm : nullptr;
+        int x_scalar = 0;
+        if (VEC) {
+            int nv = w >> 2;
+            for (int i = threadIdx.x; i < nv; i += blockDim.x) {
+                Vec4<T> qa = *reinterpret_cast<const Vec4<T> *>(ra + 4 * i);
+                Vec4<T> qb = qa;
+                if (have_b) qb = *reinterpret_cast<const Vec4<T> *>(rb + 4 * i);
+                uchar4 m;
+                m.x = one(qa.v[0], qb.v[0], have_b);
+                m.y = one(qa.v[1], qb.v[1], have_b);
+                m.z = one(qa.v[2], qb.v[2], have_b);
+                m.w = one(qa.v[3], qb.v[3], have_b);
+                cnt += m.x + m.y + m.z + m.w;
+                if (rm) *reinterpret_cast<uchar4 *>(rm + 4 * i) = m;
+            }
+            x_scalar = nv << 2;
+        }
+        for (int x = x_scalar + threadIdx.x; x < w; x += blockDim.x) {
+            uint8_t m = one(ra[x], have_b ? rb[x] : (T)0, have_b);
+            cnt += m;
+            if (rm) rm[x] = m;
+        }
+    }
+
+    // block reduction: warp shuffles, then one atomic per block
+    __shared__ A s_mn_a[8], s_mx_a[8], s_mn_b[8], s_mx_b[8];
+    __shared__ unsigned s_cnt[8];
+    mn_a = warp_min(mn_a); mx_a = warp_max(mx_a);
+    mn_b = warp_min(mn_b); mx_b = warp_max(mx_b);
+    for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (lane == 0) {
+        s_mn_a[wid] = mn_a; s_mx_a[wid] = mx_a; s_mn_b[wid] = mn_b; s_mx_b[wid] = mx_b;
+        s_cnt[wid] = cnt;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned long long c = 0;
+        for (int i = 0; i < (int)(blockDim.x >> 5); i++) {
+            mn_a = acc_min(mn_a, s_mn_a[i]); mx_a = acc_max(mx_a, s_mx_a[i]);
+            mn_b = acc_min(mn_b, s_mn_b[i]); mx_b = acc_max(mx_b, s_mx_b[i]);
+            c += s_cnt[i];
+        }
+        publish_minmax(st, slot_a, mn_a, mx_a);
+        if (have_b) publish_minmax(st, slot_b, mn_b, mx_b);
+        if (mask) atomicAdd(&st->valid, c);
+    }
+}
+
+__global__ void k_reset_stats(KrDevStats *st)
+{
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        for (int i = 0; i < 3; i++) {
+            st->min_i[i] = INT_MAX; st->max_i[i] = INT_MIN;
+            st->minf_enc[i] = 0xffffffffu; st->maxf_enc[i] = 0u;
+            st->undecided[i] = 0;
+        }
+        st->valid = 0ull;
+        st->eig_max_enc = KR_ENC_NEG_INF;
+        st->n_cand = st->n_thr = st->n_sel = st->n_acc = st->n_corners = st->n_kept = 0;
+        st->nms_rounds = st->overflow = st->select_incomplete = 0;
+        st->thr_bits = st->cut_bits = st->hist_shift = 0;
+        st->barrier[0] = st->barrier[1] = 0;
+        st->n_rowkeys = 0;
+    }
+}
+
+__global__ void k_reset_slot(KrDevStats *st, int slot)
+{
+    st->min_i[slot] = INT_MAX; st->max_i[slot] = INT_MIN;
+    st->minf_enc[slot] = 0xffffffffu; st->maxf_enc[slot] = 0u;
+}
+
+// 65 536-entry table of _to_uint8 for a 16-bit (or 8-bit) raster: entry = the
+// raw bit pattern of the pixel.  float64: subtract, divide, multiply by 255
+// (each correctly rounded, never fused), truncate -- klt.py:47-48.
+__global__ void k_build_lut(const KrDevStats *st, int slot, int dtype, int invert, uint8_t *lut)
+{
+    int bits = blockIdx.x * blockDim.x + threadIdx.x;
+    if (bits >= 65536) return;
+    int r;
+    if (dtype == KR_U8) {
+        r = bits & 255;                                 // uint8 input: _to_uint8 is a no-op
+    } else {
+        int v = (dtype == KR_I16) ? (int)(int16_t)(uint16_t)bits : bits;
+        int mn = st->min_i[slot], mx = st->max_i[slot];
+        r = 0;
+        if (mx > mn) {
+            double q = __ddiv_rn(__dsub_rn((double)v, (double)mn), (double)(mx - mn));
+            q = __dmul_rn(q, 255.0);
+            if (q >= 0.0 && q < 256.0) r = (int)q;      // values outside [mn, mx] never occur
+        }
+    }
+    if (invert) r = 255 - r;
+    lut[bits] = (uint8_t)r;
+}
+
+template <int K> struct LapCoef;
+template <> struct LapCoef<5> {
+    __device__ static constexpr int d2(int i) { constexpr int t[5] = {1, 0, -2, 0, 1}; return t[i]; }
+    __device__ static constexpr int s(int i) { constexpr int t[5] = {1, 4, 6, 4, 1}; return t[i]; }
+};
+template <> struct LapCoef<7> {
+    __device__ static constexpr int d2(int i) { constexpr int t[7] = {1, 2, -1, -4, -1, 2, 1}; return t[i]; }
+    __device__ static constexpr int s(int i) { constexpr int t[7] = {1, 6, 15, 20, 15, 6, 1}; return t[i]; }
+};
+template <> struct LapCoef<9> {
+    __device__ static constexpr int d2(int i) { constexpr int t[9] = {1, 4, 4, -4, -10, -4, 4, 4, 1}; return t[i]; }
+    __device__ static constexpr int s(int i) { constexpr int t[9] = {1, 8, 28, 56, 70, 56, 28, 8, 1}; return t[i]; }
+};
+template <> struct LapCoef<11> {
+    __device__ static constexpr int d2(int i) { constexpr int t[11] = {1, 6, 13, 8, -14, -28, -14, 8, 13, 6, 1}; return t[i]; }
+    __device__ static constexpr int s(int i) { constexpr int t[11] = {1, 10, 45, 120, 210, 252, 210, 120, 45, 10, 1}; return t[i]; }
+};
+
+// uint8 value of one raw pixel: table lookup (16/8-bit rasters, L1-resident
+// 64 KB table) or the float32 expression NumPy evaluates for float32 rasters.
+template <typename T>
+__device__ __forceinline__ int to_u8(T v, const uint8_t *__restrict__ lut, float fmn, float frange,
+                                     int invert)
+{
+    if (PixTraits<T>::is_float) {
+        int r = 0;
+        if (frange > 0.f) {
+            float q = __fmul_rn(__fdiv_rn(__fsub_rn((float)v, fmn), frange), 255.0f);
+            if (q >= 0.f && q < 256.f) r = (int)q;
+        }
+        return invert ? 255 - r : r;
+    }
+    return __ldg(lut + (uint16_t)v);       // invert is folded into the table
+}
+
+constexpr int LAP_TW = 64, LAP_TH = 32, LAP_THREADS = 256;
+
+// K2.  One block = one LAP_TW x LAP_TH output tile.  Stage the normalised uint8
+// tile (+ halo, REFLECT_101) in shared memory, then the separable integer form
+//   acc = corr(src, d2_x (x) s_y) + corr(src, s_x (x) d2_y)      (k >= 5)
+// or the 3x3 kernels of k = 1 / 3; saturate to [0, 255].
+template <int K, typename T>
+__global__ void __launch_bounds__(LAP_THREADS)
+k_laplacian(const T *__restrict__ img, int64_t pitch, int w, int h, const uint8_t *__restrict__ lut,
+            const KrDevStats *__restrict__ st, int slot, int invert, uint8_t *__restrict__ out,
+            int64_t out_pitch)
+{
+    constexpr int R = (K <= 3) ? 1 : K / 2;
+    constexpr int PW = LAP_TW + 2 * R, PH = LAP_TH + 2 * R;
+    constexpr int PWS = (PW + 3) & ~3;
+    __shared__ uint8_t pix[PH][PWS];
+    __shared__ int rd[(K <= 3) ? 1 : PH][(K <= 3) ? 1 : LAP_TW + 1];
+    __shared__ int rs[(K <= 3) ? 1 : PH][(K <= 3) ? 1 : LAP_TW + 1];
+
+    float fmn = 0.f, frange = 0.f;
+    if (PixTraits<T>::is_float) {
+        float mn = kr_f32_dec_bits(st->minf_enc[slot], 0), mx = kr_f32_dec_bits(st->maxf_enc[slot], 0);
+        fmn = mn;
+        frange = (mx > mn) ? (float)((double)mx - (double)mn) : 0.f;
+    }
+    const int x0 = blockIdx.x * LAP_TW, y0 = blockIdx.y * LAP_TH;
+    for (int i = threadIdx.x; i < PH * PW; i += LAP_THREADS) {
+        int ty = i / PW, tx = i - ty * PW;
+        int gy = kr_reflect101(y0 - R + ty, h), gx = kr_reflect101(x0 - R + tx, w);
+        const T *row = (const T *)((const char *)img + (int64_t)gy * pitch);
+        pix[ty][tx] = (uint8_t)to_u8<T>(row[gx], lut, fmn, frange, invert);
+    }
+    __syncthreads();
+
+    if (K <= 3) {
+        for (int i = threadIdx.x; i < LAP_TH * LAP_TW; i += LAP_THREADS) {
+            int ty = i / LAP_TW, tx = i - ty * LAP_TW;
+            int gx = x0 + tx, gy = y0 + ty;
+            if (gx >= w || gy >= h) continue;
+            int acc;
+            if (K == 1)
+                acc = pix[ty][tx + 1] + pix[ty + 2][tx + 1] + pix[ty + 1][tx] + pix[ty + 1][tx + 2] -
+                      4 * pix[ty + 1][tx + 1];
+            else
+                acc = 2 * (pix[ty][tx] + pix[ty][tx + 2] + pix[ty + 2][tx] + pix[ty + 2][tx + 2]) -
+                      8 * pix[ty + 1][tx + 1];
+            out[(int64_t)gy * out_pitch + gx] = (uint8_t)min(255, max(0, acc));
+        }
+    } else {
+        typedef LapCoef<(K <= 3) ? 5 : K> C;
+        for (int i = threadIdx.x; i < PH * LAP_TW; i += LAP_THREADS) {
+            int ty = i / LAP_TW, tx = i - ty * LAP_TW;
+            int ad = 0, as = 0;
+#pragma unroll
+            for (int j = 0; j < K; j++) {
+                int v = pix[ty][tx + j];
+                ad += C::d2(j) * v;
+                as += C::s(j) * v;
+            }
+            rd[ty][tx] = ad;
+            rs[ty][tx] = as;
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < LAP_TH * LAP_TW; i += LAP_THREADS) {
+            int ty = i / LAP_TW, tx = i - ty * LAP_TW;
+            int gx = x0 + tx, gy = y0 + ty;
+            if (gx >= w || gy >= h) continue;
+            int acc = 0;
+#pragma unroll
+            for (int j = 0; j < K; j++) acc += C::s(j) * rd[ty + j][tx] + C::d2(j) * rs[ty + j][tx];
+            out[(int64_t)gy * out_pitch + gx] = (uint8_t)min(255, max(0, acc));
+        }
+    }
+}
+
+template <typename T>
+int launch_minmax(kr_ctx *ctx, const void *a, int64_t pa, const void *b, int64_t pb, int w, int h,
+                  int slot_a, int slot_b, int has_nd_a, double nd_a, int has_nd_b, double nd_b,
+                  uint8_t *mask, int64_t pm, cudaStream_t s)
+{
+    const size_t va = sizeof(T) * 4;
+    bool vec = ((uintptr_t)a % va == 0) && (pa % (int64_t)va == 0);
+    if (b) vec = vec && ((uintptr_t)b % va == 0) && (pb % (int64_t)va == 0);
+    if (mask) vec = vec && ((uintptr_t)mask % 4 == 0) && (pm % 4 == 0);
+    int grid = ctx->num_sms * 8;
+    if (grid > h) grid = h;
+    if (vec)
+        k_minmax_mask<T, true><<<grid, 256, 0, s>>>((const T *)a, pa, (const T *)b, pb, w, h, slot_a,
+                                                   slot_b, has_nd_a, nd_a, has_nd_b, nd_b, mask, pm,
+                                                   ctx->d_stats);
+    else
+        k_minmax_mask<T, false><<<grid, 256, 0, s>>>((const T *)a, pa, (const T *)b, pb, w, h, slot_a,
+                                                    slot_b, has_nd_a, nd_a, has_nd_b, nd_b, mask, pm,
+                                                    ctx->d_stats);
+    KR_LAUNCH_CHECK();
+    return KR_OK;
+}
+
+int dispatch_minmax(kr_ctx *ctx, const void *a, int64_t pa, const void *b, int64_t pb, int dtype, int w,
+                    int h, int slot_a, int slot_b, int has_nd_a, double nd_a, int has_nd_b,
+                    double nd_b, uint8_t *mask, int64_t pm, cudaStream_t s)
+{
+    switch (dtype) {
+    case KR_U8: return launch_minmax<uint8_t>(ctx, a, pa, b, pb, w, h, slot_a, slot_b, has_nd_a, nd_a, has_nd_b, nd_b, mask, pm, s);
+    case KR_U16: return launch_minmax<uint16_t>(ctx, a, pa, b, pb, w, h, slot_a, slot_b, has_nd_a, nd_a, has_nd_b, nd_b, mask, pm, s);
+    case KR_I16: return launch_minmax<int16_t>(ctx, a, pa, b, pb, w, h, slot_a, slot_b, has_nd_a, nd_a, has_nd_b, nd_b, mask, pm, s);
+    case KR_F32: return launch_minmax<float>(ctx, a, pa, b, pb, w, h, slot_a, slot_b, has_nd_a, nd_a, has_nd_b, nd_b, mask, pm, s);
+    default: return kr_set_error(KR_ERR_UNSUPPORTED, "unsupported raster dtype %d", dtype);
+    }
+}
+
+template <int K, typename T>
+int launch_lap(kr_ctx *ctx, const void *img, int64_t pitch, int w, int h, int slot, int invert,
+               uint8_t *out, int64_t out_pitch, cudaStream_t s)
+{
+    dim3 grid((w + LAP_TW - 1) / LAP_TW, (h + LAP_TH - 1) / LAP_TH);
+    k_laplacian<K, T><<<grid, LAP_THREADS, 0, s>>>((const T *)img, pitch, w, h, ctx->d_lut[slot],
+                                                  ctx->d_stats, slot, invert, out, out_pitch);
+    KR_LAUNCH_CHECK();
+    return KR_OK;
+}
+
+template <typename T>
+int dispatch_lap_k(kr_ctx *ctx, const void *img, int64_t pitch, int w, int h, int slot, int ksize,
+                   int invert, uint8_t *out, int64_t out_pitch, cudaStream_t s)
+{
+    switch (ksize) {
+    case 1: return launch_lap<1, T>(ctx, img, pitch, w, h, slot, invert, out, out_pitch, s);
+    case 3: return launch_lap<3, T>(ctx, img, pitch, w, h, slot, invert, out, out_pitch, s);
+    case 5: return launch_lap<5, T>(ctx, img, pitch, w, h, slot, invert, out, out_pitch, s);
+    case 7: return launch_lap<7, T>(ctx, img, pitch, w, h, slot, invert, out, out_pitch, s);
+    case 9: return launch_lap<9, T>(ctx, img, pitch, w, h, slot, invert, out, out_pitch, s);
+    case 11: return launch_lap<11, T>(ctx, img, pitch, w, h, slot, invert, out, out_pitch, s);
+    default:
+        return kr_set_error(KR_ERR_UNSUPPORTED,
+                            "Laplacian ksize %d not supported (1,3,5,7,9,11 are)", ksize);
+    }
+}
+
+}  // namespace
+
+int krl_reset_stats(kr_ctx *ctx, cudaStream_t s)
+{
+    k_reset_stats<<<1, 32, 0, s>>>(ctx->d_stats);
+    KR_LAUNCH_CHECK();
+    return KR_OK;
+}
+
+int krl_minmax_mask(kr_ctx *ctx, const void *a, int64_t pa, const void *b, int64_t pb, int dtype, int w,
+                    int h, int has_nd_a, double nd_a, int has_nd_b, double nd_b, uint8_t *mask,
+                    int64_t pm, cudaStream_t s)
+{
+    return dispatch_minmax(ctx, a, pa, b, pb, dtype, w, h, 0, 1, has_nd_a, nd_a, has_nd_b, nd_b, mask,
+                           pm, s);
+}
+
+int krl_minmax_single(kr_ctx *ctx, const void *img, int64_t pitch, int dtype, int w, int h, int slot,
+                      cudaStream_t s)
+{
+    k_reset_slot<<<1, 1, 0, s>>>(ctx->d_stats, slot);
+    KR_LAUNCH_CHECK();
+    return dispatch_minmax(ctx, img, pitch, nullptr, 0, dtype, w, h, slot, slot, 0, 0.0, 0, 0.0,
+                           nullptr, 0, s);
+}
+
+int krl_laplacian(kr_ctx *ctx, const void *img, int64_t pitch, int dtype, int w, int h, int slot,
+                  int ksize, int invert, uint8_t *out, int64_t out_pitch, cudaStream_t s)
+{
+    if (slot < 0 || slot > 2) return kr_set_error(KR_ERR_INVALID, "bad min/max slot %d", slot);
+    if (dtype != KR_F32) {
+        k_build_lut<<<65536 / 256, 256, 0, s>>>(ctx->d_stats, slot, dtype, invert, ctx->d_lut[slot]);
+        KR_LAUNCH_CHECK();
+    }
+    switch (dtype) {
+    case KR_U8: return dispatch_lap_k<uint8_t>(ctx, img, pitch, w, h, slot, ksize, invert, out, out_pitch, s);
+    case KR_U16: return dispatch_lap_k<uint16_t>(ctx, img, pitch, w, h, slot, ksize, invert, out, out_pitch, s);
+    case KR_I16: return dispatch_lap_k<int16_t>(ctx, img, pitch, w, h, slot, ksize, invert, out, out_pitch, s);
+    case KR_F32: return dispatch_lap_k<float>(ctx, img, pitch, w, h, slot, ksize, invert, out, out_pitch, s);
+    default: return kr_set_error(KR_ERR_UNSUPPORTED, "unsupported raster dtype %d", dtype);
+    }
+}

@@ -1,0 +1,312 @@
+"""Parity of the CUDA path (through the C ABI) with the CPU oracle and the golden
+vectors of the unmodified reference + cv2 4.13 (tests/golden, oracle/make_golden.py).
+
+Bars (BASELINE.json north_star): corners bit-exact incl. order; tracked
+positions within 1e-3 px; status / back-check flags identical; ZNCC within 1e-5
+with an identical NaN pattern.  Integer stages (min/max, mask, uint8, Laplacian,
+pyrDown) are bit-exact."""
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+from conftest import conf_from_golden  # noqa: E402
+from oracle import oracle as O  # noqa: E402
+
+CASES = ["basic", "tiles_mask", "dict_inv"]
+
+
+@pytest.fixture(scope="module")
+def N():
+    from karios_b200 import _native
+    return _native
+
+
+@pytest.fixture(scope="module")
+def ctx(N):
+    c = N.Context(1024, 1024, 20000)
+    yield c
+    c.close()
+
+
+def dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def _ks(conf):
+    k = conf.laplacian_kernel_size
+    return (k["mon"], k["ref"]) if isinstance(k, dict) else (k, k)
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_minmax_mask(golden, N, ctx, name):
+    g = golden(name)
+    mon, ref = g["mon"], g["ref"]
+    mask = ctx.minmax_mask(dev(mon), dev(ref), want_mask=True)
+    st = ctx.read_stats()
+    assert (st.min_a, st.max_a, st.min_b, st.max_b) == (mon.min(), mon.max(), ref.min(), ref.max())
+    want, cnt = O.auto_mask(mon, ref)
+    assert np.array_equal(mask.cpu().numpy(), want)
+    assert st.valid == cnt
+    # nodata handling (klt.py:270-273)
+    nd = int(mon[5, 5])
+    mask2 = ctx.minmax_mask(dev(mon), dev(ref), nodata_a=nd, want_mask=True)
+    want2, cnt2 = O.auto_mask(mon, ref, nd_mon=nd)
+    assert np.array_equal(mask2.cpu().numpy(), want2) and ctx.read_stats().valid == cnt2
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_laplacian(golden, N, ctx, name):
+    g = golden(name)
+    conf = conf_from_golden(g, O.KLTConfiguration)
+    mk, rk = _ks(conf)
+    ref, mon = dev(g["ref"]), dev(g["mon"])
+    assert np.array_equal(ctx.u8_laplacian(ref, rk).cpu().numpy(), g["lap_ref"])
+    inv = conf.laplacian_invert_polarity is True
+    assert np.array_equal(ctx.u8_laplacian(mon, mk, invert=inv).cpu().numpy(), g["lap_mon"])
+    for kk in (1, 3, 5, 9, 11):
+        got = ctx.u8_laplacian(ref, kk).cpu().numpy()
+        assert np.array_equal(got, g[f"lap_ref_k{kk}"]), f"ksize {kk}: {(got != g[f'lap_ref_k{kk}']).sum()} px differ"
+    # slots filled by a previous min/max pass give the same planes
+    ctx.minmax_mask(mon, ref)
+    assert np.array_equal(ctx.u8_laplacian(ref, rk, slot=1).cpu().numpy(), g["lap_ref"])
+    assert np.array_equal(ctx.u8_laplacian(mon, mk, invert=inv, slot=0).cpu().numpy(), g["lap_mon"])
+
+
+def test_laplacian_dtypes_and_odd_shapes(N, ctx):
+    rng = np.random.default_rng(5)
+    for shape in ((1, 1), (3, 5), (5, 5), (67, 131), (200, 97)):
+        a16 = rng.integers(0, 65535, shape).astype(np.uint16)
+        for k in (1, 3, 5, 7, 9, 11):
+            want = O.laplacian(O.to_uint8(a16), k)
+            got = ctx.u8_laplacian(dev(a16), k).cpu().numpy()
+            assert np.array_equal(got, want), (shape, k)
+    a = rng.integers(0, 255, (90, 77)).astype(np.uint8)                      # uint8: no normalisation
+    assert np.array_equal(ctx.u8_laplacian(dev(a), 7).cpu().numpy(), O.laplacian(a, 7))
+    assert np.array_equal(ctx.u8_laplacian(dev(a), 5, invert=True).cpu().numpy(), O.laplacian(255 - a, 5))
+    ai = rng.integers(-2000, 9000, (90, 77)).astype(np.int16)               # int16 -> float64 scale
+    assert np.array_equal(ctx.u8_laplacian(dev(ai), 7).cpu().numpy(), O.laplacian(O.to_uint8(ai), 7))
+    af = rng.normal(100, 30, (90, 77)).astype(np.float32)                    # float32 -> float32 scale
+    assert np.array_equal(ctx.u8_laplacian(dev(af), 3).cpu().numpy(), O.laplacian(O.to_uint8(af), 3))
+    flat = np.full((40, 40), 7, np.uint16)                                   # max == min -> zeros
+    assert not ctx.u8_laplacian(dev(flat), 7).cpu().numpy().any()
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_min_eigen_val(golden, N, ctx, name):
+    g = golden(name)
+    conf = conf_from_golden(g, O.KLTConfiguration)
+    eig = ctx.corner_min_eigen_val(dev(g["lap_ref"]), conf.blocksize).cpu().numpy()
+    want = O.min_eigen_val(g["lap_ref"], conf.blocksize)
+    bad = eig != want
+    assert not bad.any(), f"{bad.sum()} of {bad.size} eigenvalues differ, first at {np.argwhere(bad)[:5]}"
+    assert eig.max() == g["eig_max"]
+    for block in (3, 4, 7, 10):
+        e = ctx.corner_min_eigen_val(dev(g["lap_ref"]), block).cpu().numpy()
+        assert np.array_equal(e, O.min_eigen_val(g["lap_ref"], block)), block
+
+
+def test_min_eigen_val_small_images(N, ctx):
+    rng = np.random.default_rng(9)
+    for shape in ((1, 1), (2, 3), (5, 5), (9, 40), (33, 65), (64, 32)):
+        a = rng.integers(0, 255, shape).astype(np.uint8)
+        for block in (3, 15):
+            e = ctx.corner_min_eigen_val(dev(a), block).cpu().numpy()
+            assert np.array_equal(e, O.min_eigen_val(a, block)), (shape, block)
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_good_features(golden, N, ctx, name):
+    g = golden(name)
+    conf = conf_from_golden(g, O.KLTConfiguration)
+    lap, mask = dev(g["lap_ref"]), dev(g["mask_box"])
+    p0 = ctx.good_features(lap, mask, conf.maxCorners, conf.qualityLevel, conf.minDistance,
+                           conf.blocksize).cpu().numpy()
+    want = g["p0"].reshape(-1, 2)
+    assert p0.shape == want.shape, (p0.shape, want.shape, ctx.read_stats().as_dict())
+    assert np.array_equal(p0, want)                      # same corners, same order
+    p0b = ctx.good_features(lap, None, 150, 0.05, 4, 7).cpu().numpy()
+    assert np.array_equal(p0b, g["p0_alt"].reshape(-1, 2))
+
+
+def test_good_features_parameter_sweep(golden, N, ctx):
+    g = golden("basic")
+    lap = g["lap_ref"]
+    eig = O.min_eigen_val(lap, 15)
+    for mc, q, md in ((0, 0.1, 10), (50, 0.3, 25.5), (1000, 0.01, 1), (1000, 0.01, 0.5),
+                      (7, 0.5, 3), (100000, 0.001, 2.5)):
+        want, _, _ = O.select_corners(eig, None, mc, q, md)
+        got = ctx.good_features(dev(lap), None, mc, q, md, 15).cpu().numpy()
+        assert got.shape == want.shape and np.array_equal(got, want), (mc, q, md, got.shape, want.shape)
+    # flat image / all-zero mask: no corners
+    z = np.zeros((50, 60), np.uint8)
+    assert ctx.good_features(dev(z), None, 100, 0.1, 10, 15).shape[0] == 0
+    assert ctx.good_features(dev(lap), dev(np.zeros_like(lap)), 100, 0.1, 10, 15).shape[0] == 0
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_pyr_down(golden, N, ctx, name):
+    g = golden(name)
+    assert np.array_equal(ctx.pyr_down(dev(g["lap_ref"])).cpu().numpy(), g["pyr_ref"])
+    for shape in ((1, 1), (2, 2), (7, 9), (51, 50), (130, 257)):
+        a = np.random.default_rng(1).integers(0, 255, shape).astype(np.uint8)
+        assert np.array_equal(ctx.pyr_down(dev(a)).cpu().numpy(), O.pyr_down(a)), shape
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_pyr_lk(golden, N, ctx, name):
+    g = golden(name)
+    conf = conf_from_golden(g, O.KLTConfiguration)
+    w = conf.matching_winsize
+    for p0k, p1k, stk, errk, a, b in (("p0", "lk_p1", "lk_st", "lk_err", "lap_ref", "lap_mon"),
+                                      ("lk_p1", "lk_p0r", "lk_st2", "lk_err2", "lap_mon", "lap_ref"),
+                                      ("lkb_p0", "lkb_p1", "lkb_st", "lkb_err", "lap_ref", "lap_mon")):
+        p1, st, err = ctx.pyr_lk(dev(g[a]), dev(g[b]), dev(g[p0k].reshape(-1, 2)), win=w)
+        p1, st, err = p1.cpu().numpy(), st.cpu().numpy(), err.cpu().numpy()
+        # (1) against the oracle with exact integer sums: the same arithmetic, bit for bit
+        o1, ost, oerr = O.pyr_lk(g[a], g[b], g[p0k], win=w, acc_mode=0)
+        assert np.array_equal(st, ost.ravel()), (name, p0k)
+        assert np.array_equal(p1, o1.reshape(-1, 2)), np.abs(p1 - o1.reshape(-1, 2)).max()
+        ok = st == 1
+        assert np.array_equal(err[ok], oerr.ravel()[ok])
+        # (2) against cv2 (golden): north-star tolerances
+        assert np.array_equal(st, g[stk].ravel())
+        d = np.abs(p1 - g[p1k].reshape(-1, 2)).max(-1)
+        assert d.max() < 1e-3
+        e_ref = g[errk].ravel()[ok]
+        assert (np.abs(err[ok] - e_ref) <= 2e-3 * np.maximum(1.0, e_ref)).all()
+
+
+def test_pyr_lk_windows_and_small_images(N, ctx):
+    rng = np.random.default_rng(2)
+    base = rng.integers(0, 255, (120, 140)).astype(np.uint8)
+    import scipy.ndimage as ndi
+    a = ndi.gaussian_filter(base.astype(np.float32), 2.0)
+    a = ((a - a.min()) / (a.max() - a.min()) * 255).astype(np.uint8)
+    b = np.roll(a, (1, -1), (0, 1))
+    pts = np.stack([rng.uniform(-5, 145, 200), rng.uniform(-5, 125, 200)], -1).astype(np.float32)
+    for win, lvl in ((5, 1), (15, 2), (21, 0), (29, 3), (25, 1)):
+        o1, ost, oerr = O.pyr_lk(a, b, pts.reshape(-1, 1, 2), win=win, max_level=lvl, acc_mode=0)
+        p1, st, err = ctx.pyr_lk(dev(a), dev(b), dev(pts), win=win, max_level=lvl)
+        assert np.array_equal(st.cpu().numpy(), ost.ravel()), (win, lvl)
+        assert np.array_equal(p1.cpu().numpy(), o1.reshape(-1, 2)), (win, lvl)
+    small_a, small_b = a[:40, :45].copy(), b[:40, :45].copy()       # no second level (<= win)
+    o1, ost, _ = O.pyr_lk(small_a, small_b, pts[:50].reshape(-1, 1, 2), win=25, acc_mode=0)
+    p1, st, _ = ctx.pyr_lk(dev(small_a), dev(small_b), dev(pts[:50]), win=25)
+    assert np.array_equal(st.cpu().numpy(), ost.ravel()) and np.array_equal(p1.cpu().numpy(), o1.reshape(-1, 2))
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_klt_tracker(golden, name):
+    """The drop-in klt_tracker (klt.py:83-172) against the unmodified reference's output."""
+    from karios_b200.matcher.klt import klt_tracker
+    from karios_b200.core.configuration import KLTConfiguration
+    g = golden(name)
+    conf = conf_from_golden(g, KLTConfiguration)
+    df, ninit = klt_tracker(g["lap_ref"], g["lap_mon"], g["mask_box"], conf)
+    assert ninit == int(g["trk_ninit"])
+    assert list(df.columns) == ["x0", "y0", "dx", "dy", "score"]
+    assert all(str(t) == "float32" for t in df.dtypes)
+    assert len(df) == len(g["trk_x0"])                     # identical back-check decisions
+    assert np.array_equal(df["x0"].to_numpy(), g["trk_x0"]) and np.array_equal(df["y0"].to_numpy(), g["trk_y0"])
+    assert np.abs(df["dx"].to_numpy() - g["trk_dx"]).max() < 1e-3
+    assert np.abs(df["dy"].to_numpy() - g["trk_dy"]).max() < 1e-3
+    assert np.abs(df["score"].to_numpy() - g["trk_score"]).max() < 2e-2
+    # p0 given: mask ignored, same result (klt.py:109-120)
+    df2, n2 = klt_tracker(g["lap_ref"], g["lap_mon"], None, conf, p0=g["p0"])
+    assert n2 == ninit and np.array_equal(df2["x0"].to_numpy(), df["x0"].to_numpy())
+    assert np.array_equal(df2["dx"].to_numpy(), df["dx"].to_numpy())
+
+
+def test_klt_tracker_no_features():
+    from karios_b200.matcher.klt import klt_tracker
+    from karios_b200.core.configuration import KLTConfiguration
+    z = np.zeros((64, 64), np.uint8)
+    assert klt_tracker(z, z, np.ones_like(z), KLTConfiguration()) is None
+
+
+@pytest.mark.parametrize("name", CASES)
+@pytest.mark.parametrize("resident", [False, True])
+def test_klt_match(golden, name, resident):
+    """KLT.match (klt.py:198-349): tiling, masks, offsets, order -- host rasters and
+    rasters resident in HBM."""
+    from karios_b200.matcher.klt import KLT
+    from karios_b200.core.configuration import KLTConfiguration
+    from karios_b200.core.image import ArrayRaster, DeviceRaster
+    g = golden(name)
+    conf = conf_from_golden(g, KLTConfiguration)
+    mk = (lambda a: DeviceRaster(dev(a))) if resident else ArrayRaster
+    mask = mk(g["mask"]) if "mask" in g.files else None
+    frames = list(KLT(conf).match(mk(g["mon"]), mk(g["ref"]), mask))
+    assert len(frames) == int(g["match_ntiles"])
+    for i, f in enumerate(frames):
+        assert len(f) == len(g[f"match{i}_x0"]), (i, len(f), len(g[f"match{i}_x0"]))
+        assert np.array_equal(f["x0"].to_numpy(), g[f"match{i}_x0"])
+        assert np.array_equal(f["y0"].to_numpy(), g[f"match{i}_y0"])
+        assert np.abs(f["dx"].to_numpy() - g[f"match{i}_dx"]).max() < 1e-3
+        assert np.abs(f["dy"].to_numpy() - g[f"match{i}_dy"]).max() < 1e-3
+        assert np.abs(f["score"].to_numpy() - g[f"match{i}_score"]).max() < 2e-2
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_zncc(golden, name):
+    import pandas as pd
+    from karios_b200.matcher.zncc_service import ZNCCService
+    from karios_b200.core.image import ArrayRaster
+    g = golden(name)
+    df = pd.DataFrame({c: g["all_" + c] for c in ("x0", "y0", "dx", "dy", "score")})
+    df.index = df.index + 7                       # the result must carry the caller's index
+    z = ZNCCService().compute_zncc(df, ArrayRaster(g["mon"]), ArrayRaster(g["ref"]))
+    assert z.index.equals(df.index) and z.dtype == np.float64
+    zr = g["zncc"]
+    assert np.array_equal(np.isnan(z.to_numpy()), np.isnan(zr))
+    ok = ~np.isnan(zr)
+    assert np.abs(z.to_numpy()[ok] - zr[ok]).max() < 1e-5
+    zo = O.zncc(g["all_x0"], g["all_y0"], g["all_dx"], g["all_dy"], g["mon"], g["ref"])
+    assert np.array_equal(z.to_numpy()[ok], zo[ok])        # same arithmetic as the oracle
+
+
+def test_zncc_known_answers(golden, N, ctx):
+    """tests/test_zncc_service.py / test_zncc_zero_std_fix.py of the reference, through kr_zncc."""
+    g = golden("zncc_known")
+    a, b = g["a"], g["b"]
+    f = lambda v: torch.tensor([v], dtype=torch.float32, device="cuda")  # noqa: E731
+
+    def one(p, q, x=28.0, y=28.0, dx=0.0, dy=0.0):
+        return float(ctx.zncc(dev(p), dev(q), f(x), f(y), f(dx), f(dy)).cpu()[0])
+    assert abs(one(a, b) - float(g["z_ab"])) < 1e-12
+    assert abs(one(a, a) - 1.0) < 1e-12
+    assert abs(one(a, (65535 - a).astype(np.uint16)) + 1.0) < 1e-12
+    assert np.isnan(one(np.full((57, 57), 1234, np.uint16), b))
+    assert np.isnan(one(a, b, x=27.0)) and np.isnan(one(a, b, y=29.0))
+    big = np.random.default_rng(0).integers(1, 60000, (90, 90)).astype(np.uint16)
+    for dx, want in ((0.5, 40), (1.5, 42), (-0.5, 40), (2.5, 42)):            # half to even
+        z = one(big, big, 40.0, 40.0, dx, 0.0)
+        assert abs(z - O.zncc2(big, big, 40, 40, 40, want, 21)) < 1e-12
+    # other dtypes
+    a8, b8 = (a >> 8).astype(np.uint8), (b >> 8).astype(np.uint8)
+    assert abs(one(a8, b8) - O.zncc2(a8, b8, 28, 28, 28, 28, 21)) < 1e-12
+    af, bf = a.astype(np.float32) * 0.37, b.astype(np.float32) * 1.7 - 5
+    assert abs(one(af, bf) - O.zncc2(af.astype(np.float64), bf.astype(np.float64), 28, 28, 28, 28, 21)) < 1e-9
+
+
+def test_sort_and_unlimited_corners(N):
+    """maxCorners = 0 exercises the multi-chunk sort and the full NMS."""
+    from karios_b200 import synth
+    ref_t, _ = synth.make_pair(900, 1000, seed=3)
+    ref = ref_t.view(torch.int16).numpy().view(np.uint16)
+    lap = O.laplacian(O.to_uint8(ref), 7)
+    c = N.Context(1000, 900, 0)
+    try:
+        got = c.good_features(dev(lap), None, 0, 0.01, 3, 15).cpu().numpy()
+    finally:
+        c.close()
+    want, _, _ = O.select_corners(O.min_eigen_val(lap, 15), None, 0, 0.01, 3)
+    assert got.shape == want.shape and np.array_equal(got, want), (got.shape, want.shape)
+    assert len(want) > 3 * 8192
+
+
+def test_smoke_entry():
+    import __graft_entry__ as ge
+    ge.smoke()
