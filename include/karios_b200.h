@@ -186,6 +186,16 @@ KR_API int kr_match_tile(kr_ctx *ctx, const void *mon, int64_t mon_pitch, const 
                          int has_nodata_mon, double nodata_mon, int has_nodata_ref,
                          double nodata_ref, const kr_klt_conf *conf, kr_rows rows, void *stream);
 
+/* Measurement hooks (no reference counterpart).  With profiling on, kr_match_tile
+ * brackets its stages with CUDA events on the caller's stream; after the stream
+ * has been synchronised kr_read_stage_ms returns the KR_NUM_STAGES durations
+ * (ms) of the last call, in this order: min/max+mask, Laplacian mon, Laplacian
+ * ref, corner response, candidate selection, NMS, corner sort, pyramids, LK
+ * round trip, row compaction+sort, ZNCC. */
+#define KR_NUM_STAGES 11
+KR_API int kr_set_profiling(kr_ctx *ctx, int on);
+KR_API int kr_read_stage_ms(kr_ctx *ctx, float *ms);
+
 #ifdef __cplusplus
 }
 #endif

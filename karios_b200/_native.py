@@ -23,7 +23,11 @@ EXPORTS = [
     "kr_version", "kr_last_error", "kr_ctx_create", "kr_ctx_destroy", "kr_read_stats",
     "kr_set_select_all", "kr_minmax_mask", "kr_u8_laplacian", "kr_corner_min_eigen_val",
     "kr_good_features", "kr_pyr_down", "kr_pyr_lk", "kr_klt_track", "kr_zncc", "kr_match_tile",
+    "kr_set_profiling", "kr_read_stage_ms",
 ]
+NUM_STAGES = 11
+STAGE_NAMES = ["minmax_mask", "laplacian_mon", "laplacian_ref", "corner_response", "select",
+               "nms", "corner_sort", "pyramids", "lk_roundtrip", "rows", "zncc"]
 
 
 class KltConf(C.Structure):
@@ -80,6 +84,8 @@ def load_library(path: str = LIB_PATH):
         L.kr_ctx_destroy.restype = None
         L.kr_read_stats.argtypes = [vp, vp, C.POINTER(Stats)]
         L.kr_set_select_all.argtypes = [vp, i32]
+        L.kr_set_profiling.argtypes = [vp, i32]
+        L.kr_read_stage_ms.argtypes = [vp, C.POINTER(C.c_float)]
         L.kr_minmax_mask.argtypes = [vp, vp, i64, vp, i64, i32, i32, i32, i32, f64, i32, f64, vp, i64, vp]
         L.kr_u8_laplacian.argtypes = [vp, vp, i64, i32, i32, i32, i32, i32, i32, vp, i64, vp]
         L.kr_corner_min_eigen_val.argtypes = [vp, vp, i64, i32, i32, i32, i32, vp, i64, vp]
@@ -234,6 +240,15 @@ class Context:
             raise KariosB200Error("candidate list overflowed the context capacity "
                                   "(create the Context for a larger tile)")
         return s
+
+    def set_profiling(self, on: bool):
+        _check(self.lib.kr_set_profiling(self._h, int(bool(on))))
+
+    def stage_ms(self):
+        """Durations (ms) of the stages of the last match_tile (after a synchronise)."""
+        buf = (C.c_float * NUM_STAGES)()
+        _check(self.lib.kr_read_stage_ms(self._h, buf))
+        return dict(zip(STAGE_NAMES, list(buf)))
 
     def set_select_all(self, on: bool):
         _check(self.lib.kr_set_select_all(self._h, int(bool(on))))

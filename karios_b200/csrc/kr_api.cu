@@ -96,14 +96,17 @@ int track_common(kr_ctx *ctx, const uint8_t *ref, int64_t ref_pitch, const uint8
     KrLkArgs a;
     memset(&a, 0, sizeof(a));
     KR_TRY(krl_build_pyramids(ctx, ref, ref_pitch, mon, mon_pitch, w, h, c->win_size, c->max_level, &a, s));
+    KR_MARK(ctx, 8, s);
     a.max_count = c->max_count;
     a.eps2 = c->eps * c->eps;
     a.min_eig_thr = (float)c->min_eig_threshold;
     const float back_thr = (float)c->back_threshold;
     KR_TRY(krl_lk_roundtrip(a, ctx->d_p0, n_cap, &ctx->d_stats->n_corners, back_thr, ctx->d_p1,
                             ctx->d_d, ctx->d_keep, s));
+    KR_MARK(ctx, 9, s);
     KR_TRY(krl_emit_rows(ctx, ctx->d_p0, ctx->d_p1, ctx->d_d, ctx->d_keep, n_cap,
                          &ctx->d_stats->n_corners, sort_xy, back_thr, x_off, y_off, rows, s));
+    KR_MARK(ctx, 10, s);
     return KR_OK;
 }
 
@@ -199,6 +202,7 @@ KR_API void kr_ctx_destroy(kr_ctx *c)
     cudaFree(c->d_mask); cudaFree(c->d_lap[0]); cudaFree(c->d_lap[1]);
     for (int l = 1; l < KR_MAX_LEVELS; l++) { cudaFree(c->d_pyr[0][l]); cudaFree(c->d_pyr[1][l]); }
     cudaFree(c->d_p0); cudaFree(c->d_p1); cudaFree(c->d_d); cudaFree(c->d_keep);
+    if (c->ev[0]) for (int i = 0; i <= KR_NUM_STAGES; i++) cudaEventDestroy(c->ev[i]);
     delete c;
 }
 
@@ -206,6 +210,27 @@ KR_API int kr_set_select_all(kr_ctx *ctx, int on)
 {
     if (!ctx) return kr_set_error(KR_ERR_INVALID, "ctx is NULL");
     ctx->force_select_all = on ? 1 : 0;
+    return KR_OK;
+}
+
+KR_API int kr_set_profiling(kr_ctx *ctx, int on)
+{
+    if (!ctx) return kr_set_error(KR_ERR_INVALID, "ctx is NULL");
+    if (on && !ctx->ev[0])
+        for (int i = 0; i <= KR_NUM_STAGES; i++) KR_CUDA(cudaEventCreate(&ctx->ev[i]));
+    ctx->prof_on = on ? 1 : 0;
+    return KR_OK;
+}
+
+KR_API int kr_read_stage_ms(kr_ctx *ctx, float *ms)
+{
+    if (!ctx || !ms) return kr_set_error(KR_ERR_INVALID, "NULL argument");
+    if (!ctx->ev[0]) return kr_set_error(KR_ERR_INVALID, "profiling was never enabled");
+    for (int i = 0; i < KR_NUM_STAGES; i++) {
+        ms[i] = 0.f;
+        cudaError_t e = cudaEventElapsedTime(&ms[i], ctx->ev[i], ctx->ev[i + 1]);
+        if (e != cudaSuccess) { cudaGetLastError(); ms[i] = -1.f; }
+    }
     return KR_OK;
 }
 
@@ -364,14 +389,18 @@ KR_API int kr_match_tile(kr_ctx *ctx, const void *mon, int64_t mon_pitch, const 
     const uint8_t *mask_t = mask ? mask + (int64_t)y_off * mask_pitch + x_off : nullptr;
 
     KR_TRY(krl_reset_stats(ctx, s));
+    KR_MARK(ctx, 0, s);
     // a = monitored (slot 0), b = reference (slot 1); the auto mask only without a user mask
     KR_TRY(krl_minmax_mask(ctx, mon_t, mon_pitch, ref_t, ref_pitch, dtype, tile_w, tile_h,
                            has_nodata_mon, nodata_mon, has_nodata_ref, nodata_ref,
                            mask ? nullptr : ctx->d_mask, ctx->plane_pitch, s));
+    KR_MARK(ctx, 1, s);
     KR_TRY(krl_laplacian(ctx, mon_t, mon_pitch, dtype, tile_w, tile_h, 0, conf->ksize_mon,
                          conf->invert_mon, ctx->d_lap[0], ctx->plane_pitch, s));
+    KR_MARK(ctx, 2, s);
     KR_TRY(krl_laplacian(ctx, ref_t, ref_pitch, dtype, tile_w, tile_h, 1, conf->ksize_ref, 0,
                          ctx->d_lap[1], ctx->plane_pitch, s));
+    KR_MARK(ctx, 3, s);
     const uint8_t *m = mask ? mask_t : ctx->d_mask;
     const int64_t mp = mask ? mask_pitch : ctx->plane_pitch;
     KR_TRY(track_common(ctx, ctx->d_lap[1], ctx->plane_pitch, ctx->d_lap[0], ctx->plane_pitch, m, mp,
@@ -380,6 +409,7 @@ KR_API int kr_match_tile(kr_ctx *ctx, const void *mon, int64_t mon_pitch, const 
         KR_TRY(krl_zncc(ref, ref_pitch, img_w, img_h, mon, mon_pitch, img_w, img_h, dtype, rows.x0,
                         rows.y0, rows.dx, rows.dy, rows.score, (float)conf->zncc_min_score,
                         rows.capacity, &ctx->d_stats->n_kept, rows.zncc, s));
+    KR_MARK(ctx, 11, s);
     return KR_OK;
 }
 

@@ -539,6 +539,7 @@ int krl_good_features(kr_ctx *ctx, const uint8_t *img, int64_t pitch, const uint
                                                    tail_start, eig_out, eig_pitch, ctx->d_cand,
                                                    (uint32_t)ctx->cand_cap, ctx->d_stats, emit);
     KR_LAUNCH_CHECK();
+    KR_MARK(ctx, 4, s);
     if (!emit) return KR_OK;
 
     const uint32_t cap = (uint32_t)ctx->cand_cap;
@@ -552,6 +553,7 @@ int krl_good_features(kr_ctx *ctx, const uint8_t *img, int64_t pitch, const uint
     KR_LAUNCH_CHECK();
     k_select<<<sgrid, 256, 0, s>>>(ctx->d_cand, ctx->d_keys_a, ctx->d_stats, cap, cap);
     KR_LAUNCH_CHECK();
+    KR_MARK(ctx, 5, s);
 
     if (min_distance >= 1.0) {
         int cell = (int)rint(min_distance);
@@ -588,12 +590,14 @@ int krl_good_features(kr_ctx *ctx, const uint8_t *img, int64_t pitch, const uint
         k_accept_all<<<sgrid, 256, 0, s>>>(ctx->d_keys_a, ctx->d_keys_b, ctx->d_stats, cap);
         KR_LAUNCH_CHECK();
     }
+    KR_MARK(ctx, 6, s);
     // order by (value desc, address desc) = descending 64-bit key
     KR_TRY(krl_sort_u64(ctx, ctx->d_keys_b, ctx->d_keys_a, &ctx->d_stats->n_acc, ctx->cand_cap, 1, s));
     k_emit_corners<<<sgrid, 256, 0, s>>>(ctx->d_keys_a, ctx->d_stats, w,
                                         (max_corners > 0) ? (uint32_t)max_corners : 0u,
                                         (uint32_t)capacity, out_xy, d_count, cap);
     KR_LAUNCH_CHECK();
+    KR_MARK(ctx, 7, s);
     return KR_OK;
 }
 

@@ -58,6 +58,8 @@ struct kr_ctx {
     int nms_grid;           // co-resident grid of the persistent NMS kernel
     int force_select_all;   // sort every candidate above the threshold (no pre-selection)
     int last_dtype;         // dtype of the last min/max pass (for kr_read_stats)
+    int prof_on;            // stage events enabled (kr_set_profiling)
+    cudaEvent_t ev[KR_NUM_STAGES + 1];
 };
 
 // ---- error plumbing (kr_api.cu) ------------------------------------------
@@ -74,6 +76,12 @@ int kr_set_error(int code, const char *fmt, ...);
     do {                             \
         int _r = (expr);             \
         if (_r != KR_OK) return _r;  \
+    } while (0)
+
+// stage boundary i (see KR_NUM_STAGES in the header)
+#define KR_MARK(ctx, i, s)                                              \
+    do {                                                                \
+        if ((ctx)->prof_on) KR_CUDA(cudaEventRecord((ctx)->ev[(i)], (s))); \
     } while (0)
 
 // ---- small device helpers ------------------------------------------------

@@ -149,3 +149,23 @@ def test_round_half_even_of_float32_sum():
         z = O.zncc([x0], [x0], [dx], [np.float32(0)], img, img)[0]
         zr = O.zncc2(img, img, 40, 40, 40, want, 21)
         assert abs(z - zr) < 1e-12
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_cv2_path_matches_golden(golden, name):
+    """oracle/cv2_path.py (the cv2-based restatement timed as the CPU baseline)
+    reproduces the unmodified reference's KLT.match + compute_zncc output."""
+    from oracle import cv2_path as P
+    if not P.HAVE_CV2:
+        pytest.skip("cv2 not importable")
+    g = golden(name)
+    conf = conf_from_golden(g, O.KLTConfiguration)
+    mask = g["mask"] if "mask" in g.files else None
+    tiles, total = P.match_scene(g["mon"], g["ref"], mask, conf, zncc_threshold=-1.0)
+    assert len(tiles) == int(g["match_ntiles"]) and total == len(g["zncc"])
+    for i, t in enumerate(tiles):
+        for c in ("x0", "y0", "dx", "dy", "score"):
+            assert np.array_equal(t[c], g[f"match{i}_{c}"]), (i, c)
+    z = np.concatenate([t["zncc"] for t in tiles])
+    assert np.array_equal(np.isnan(z), np.isnan(g["zncc"]))
+    assert np.nanmax(np.abs(z - g["zncc"])) < 1e-12
