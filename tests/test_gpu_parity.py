@@ -299,10 +299,10 @@ def test_sort_and_unlimited_corners(N):
     lap = O.laplacian(O.to_uint8(ref), 7)
     c = N.Context(1000, 900, 0)
     try:
-        got = c.good_features(dev(lap), None, 0, 0.01, 3, 15).cpu().numpy()
+        got = c.good_features(dev(lap), None, 0, 0.01, 2, 15).cpu().numpy()
     finally:
         c.close()
-    want, _, _ = O.select_corners(O.min_eigen_val(lap, 15), None, 0, 0.01, 3)
+    want, _, _ = O.select_corners(O.min_eigen_val(lap, 15), None, 0, 0.01, 2)
     assert got.shape == want.shape and np.array_equal(got, want), (got.shape, want.shape)
     assert len(want) > 3 * 8192
 
