@@ -24,8 +24,7 @@
 namespace {
 
 // ---------------------------------------------------------------- K5 pyrDown
-constexpr int PD_TW = 64, PD_TH = 16, PD_THREADS = 256;
-constexpr int PD_IW = 2 * PD_TW + 3, PD_IH = 2 * PD_TH + 3;
+constexpr int PD_WARPS = 8, PD_ROWS = 32, PD_VALID = 30;
 
 struct PyrPair {
     const uint8_t *src[2];
@@ -33,35 +32,43 @@ struct PyrPair {
     int64_t src_pitch[2], dst_pitch[2];
 };
 
-__global__ void __launch_bounds__(PD_THREADS) k_pyr_down(PyrPair pp, int w, int h)
+// cv::pyrDown: [1,4,6,4,1] x [1,4,6,4,1], REFLECT_101, (sum + 128) >> 8, output
+// ((w+1)/2, (h+1)/2).  One warp walks down a strip of 30 output columns: lane <->
+// output column, each input row is two byte loads per lane (columns 2x, 2x+1),
+// the horizontal taps of the neighbours come from two warp shuffles of the
+// packed pair, the five vertical taps slide through registers (two new input
+// rows per output row).  No shared memory.
+__global__ void __launch_bounds__(PD_WARPS * 32) k_pyr_down(PyrPair pp, int w, int h)
 {
-    __shared__ uint8_t pix[PD_IH][PD_IW + 1];
-    __shared__ uint16_t hs[PD_IH][PD_TW];
+    constexpr unsigned FULL = 0xffffffffu;
     const uint8_t *__restrict__ src = pp.src[blockIdx.z];
     uint8_t *__restrict__ dst = pp.dst[blockIdx.z];
     const int64_t sp = pp.src_pitch[blockIdx.z], dp = pp.dst_pitch[blockIdx.z];
     const int dw = (w + 1) >> 1, dh = (h + 1) >> 1;
-    const int ox = blockIdx.x * PD_TW, oy = blockIdx.y * PD_TH;
-    const int ix0 = 2 * ox - 2, iy0 = 2 * oy - 2;
-    for (int i = threadIdx.x; i < PD_IH * PD_IW; i += PD_THREADS) {
-        int ty = i / PD_IW, tx = i - ty * PD_IW;
-        int gy = kr_reflect101(iy0 + ty, h), gx = kr_reflect101(ix0 + tx, w);
-        pix[ty][tx] = __ldg(src + (int64_t)gy * sp + gx);
-    }
-    __syncthreads();
-    for (int i = threadIdx.x; i < PD_IH * PD_TW; i += PD_THREADS) {
-        int ty = i / PD_TW, tx = i - ty * PD_TW;
-        const uint8_t *p = &pix[ty][2 * tx];
-        hs[ty][tx] = (uint16_t)(p[0] + p[4] + 4 * (p[1] + p[3]) + 6 * p[2]);
-    }
-    __syncthreads();
-    for (int i = threadIdx.x; i < PD_TH * PD_TW; i += PD_THREADS) {
-        int ty = i / PD_TW, tx = i - ty * PD_TW;
-        int gx = ox + tx, gy = oy + ty;
-        if (gx >= dw || gy >= dh) continue;
-        int r = 2 * ty;
-        int acc = hs[r][tx] + hs[r + 4][tx] + 4 * (hs[r + 1][tx] + hs[r + 3][tx]) + 6 * hs[r + 2][tx];
-        dst[(int64_t)gy * dp + gx] = (uint8_t)((acc + 128) >> 8);
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int xs = (blockIdx.x * PD_WARPS + wid) * PD_VALID;
+    if (xs >= dw) return;
+    const int oys = blockIdx.y * PD_ROWS, oye = min(oys + PD_ROWS, dh);
+    const int ox = xs + lane - 1;
+    const int c0 = kr_reflect101(2 * ox, w), c1 = kr_reflect101(2 * ox + 1, w);
+    const bool store_lane = lane >= 1 && lane <= PD_VALID && ox < dw;
+
+    auto hrow = [&](int r) -> int {
+        const uint8_t *row = src + (int64_t)kr_reflect101(r, h) * sp;
+        int a0 = __ldg(row + c0), a1 = __ldg(row + c1);
+        int pk = a0 | (a1 << 8);
+        int lp = __shfl_up_sync(FULL, pk, 1), rp = __shfl_down_sync(FULL, pk, 1);
+        // p(2x-2) + 4 p(2x-1) + 6 p(2x) + 4 p(2x+1) + p(2x+2)
+        return (lp & 255) + 4 * (lp >> 8) + 6 * a0 + 4 * a1 + (rp & 255);
+    };
+
+    int r = 2 * oys - 2;
+    int h0 = hrow(r), h1 = hrow(r + 1), h2 = hrow(r + 2);
+    for (int oy = oys; oy < oye; oy++) {
+        int h3 = hrow(2 * oy + 1), h4 = hrow(2 * oy + 2);
+        int acc = h0 + h4 + 4 * (h1 + h3) + 6 * h2;
+        if (store_lane) dst[(int64_t)oy * dp + ox] = (uint8_t)((acc + 128) >> 8);
+        h0 = h2; h1 = h3; h2 = h4;
     }
 }
 
@@ -382,8 +389,8 @@ int krl_pyr_down(const uint8_t *src, int64_t pitch, int w, int h, uint8_t *dst, 
     pp.src[0] = pp.src[1] = src; pp.dst[0] = pp.dst[1] = dst;
     pp.src_pitch[0] = pp.src_pitch[1] = pitch; pp.dst_pitch[0] = pp.dst_pitch[1] = dst_pitch;
     int dw = (w + 1) / 2, dh = (h + 1) / 2;
-    dim3 grid((dw + PD_TW - 1) / PD_TW, (dh + PD_TH - 1) / PD_TH, 1);
-    k_pyr_down<<<grid, PD_THREADS, 0, s>>>(pp, w, h);
+    dim3 grid((dw + PD_WARPS * PD_VALID - 1) / (PD_WARPS * PD_VALID), (dh + PD_ROWS - 1) / PD_ROWS, 1);
+    k_pyr_down<<<grid, PD_WARPS * 32, 0, s>>>(pp, w, h);
     KR_LAUNCH_CHECK();
     return KR_OK;
 }
@@ -415,8 +422,8 @@ int krl_build_pyramids(kr_ctx *ctx, const uint8_t *prev, int64_t pp, const uint8
         q.dst[0] = ctx->d_pyr[0][l + 1]; q.dst[1] = ctx->d_pyr[1][l + 1];
         q.src_pitch[0] = a->pitch[0][l]; q.src_pitch[1] = a->pitch[1][l];
         q.dst_pitch[0] = q.dst_pitch[1] = pitch;
-        dim3 grid((nw + PD_TW - 1) / PD_TW, (nh + PD_TH - 1) / PD_TH, 2);
-        k_pyr_down<<<grid, PD_THREADS, 0, s>>>(q, a->w[l], a->h[l]);
+        dim3 grid((nw + PD_WARPS * PD_VALID - 1) / (PD_WARPS * PD_VALID), (nh + PD_ROWS - 1) / PD_ROWS, 2);
+        k_pyr_down<<<grid, PD_WARPS * 32, 0, s>>>(q, a->w[l], a->h[l]);
         KR_LAUNCH_CHECK();
         levels = l + 1;
     }

@@ -182,24 +182,6 @@ __global__ void k_build_lut(const KrDevStats *st, int slot, int dtype, int inver
     lut[bits] = (uint8_t)r;
 }
 
-template <int K> struct LapCoef;
-template <> struct LapCoef<5> {
-    __device__ static constexpr int d2(int i) { constexpr int t[5] = {1, 0, -2, 0, 1}; return t[i]; }
-    __device__ static constexpr int s(int i) { constexpr int t[5] = {1, 4, 6, 4, 1}; return t[i]; }
-};
-template <> struct LapCoef<7> {
-    __device__ static constexpr int d2(int i) { constexpr int t[7] = {1, 2, -1, -4, -1, 2, 1}; return t[i]; }
-    __device__ static constexpr int s(int i) { constexpr int t[7] = {1, 6, 15, 20, 15, 6, 1}; return t[i]; }
-};
-template <> struct LapCoef<9> {
-    __device__ static constexpr int d2(int i) { constexpr int t[9] = {1, 4, 4, -4, -10, -4, 4, 4, 1}; return t[i]; }
-    __device__ static constexpr int s(int i) { constexpr int t[9] = {1, 8, 28, 56, 70, 56, 28, 8, 1}; return t[i]; }
-};
-template <> struct LapCoef<11> {
-    __device__ static constexpr int d2(int i) { constexpr int t[11] = {1, 6, 13, 8, -14, -28, -14, 8, 13, 6, 1}; return t[i]; }
-    __device__ static constexpr int s(int i) { constexpr int t[11] = {1, 10, 45, 120, 210, 252, 210, 120, 45, 10, 1}; return t[i]; }
-};
-
 // uint8 value of one raw pixel: table lookup (16/8-bit rasters, L1-resident
 // 64 KB table) or the float32 expression NumPy evaluates for float32 rasters.
 template <typename T>
@@ -217,24 +199,28 @@ __device__ __forceinline__ int to_u8(T v, const uint8_t *__restrict__ lut, float
     return __ldg(lut + (uint16_t)v);       // invert is folded into the table
 }
 
-constexpr int LAP_TW = 64, LAP_TH = 32, LAP_THREADS = 256;
+constexpr int LAP_WARPS = 8, LAP_ROWS = 64;
 
-// K2.  One block = one LAP_TW x LAP_TH output tile.  Stage the normalised uint8
-// tile (+ halo, REFLECT_101) in shared memory, then the separable integer form
-//   acc = corr(src, d2_x (x) s_y) + corr(src, s_x (x) d2_y)      (k >= 5)
-// or the 3x3 kernels of k = 1 / 3; saturate to [0, 255].
+// K2.  cv2.Laplacian's k x k kernel factorises exactly (integers, no rounding):
+//   d2 (x) s + s (x) d2 = B^(k-3)_x B^(k-3)_y M3,   B = [1,1],
+//   M3 = [[2,0,2],[0,-8,0],[2,0,2]]  (= the k = 3 kernel),
+// because d2 = [1,-2,1] * B^(k-3) and s = [1,2,1] * B^(k-3).  So the result is
+// a binomial smoothing S of the uint8 image followed by
+//   out(x,y) = 2 (E(y-1) + E(y+1)) - 8 S(x,y),   E(y) = S(x-1,y) + S(x+1,y).
+// One warp walks down a strip of 32 - 2R columns (R = k/2): lane <-> column, one
+// coalesced raw-pixel load per row, the horizontal [1,1] cascade through warp
+// shuffles, the vertical cascade and the 3-row window in registers.  No shared
+// memory, no block synchronisation; the normalisation is the L1-resident table.
 template <int K, typename T>
-__global__ void __launch_bounds__(LAP_THREADS)
+__global__ void __launch_bounds__(LAP_WARPS * 32)
 k_laplacian(const T *__restrict__ img, int64_t pitch, int w, int h, const uint8_t *__restrict__ lut,
             const KrDevStats *__restrict__ st, int slot, int invert, uint8_t *__restrict__ out,
             int64_t out_pitch)
 {
     constexpr int R = (K <= 3) ? 1 : K / 2;
-    constexpr int PW = LAP_TW + 2 * R, PH = LAP_TH + 2 * R;
-    constexpr int PWS = (PW + 3) & ~3;
-    __shared__ uint8_t pix[PH][PWS];
-    __shared__ int rd[(K <= 3) ? 1 : PH][(K <= 3) ? 1 : LAP_TW + 1];
-    __shared__ int rs[(K <= 3) ? 1 : PH][(K <= 3) ? 1 : LAP_TW + 1];
+    constexpr int NS = (K <= 3) ? 0 : K - 3;          // [1,1] stages per dimension (even)
+    constexpr int VALID = 32 - 2 * R;
+    constexpr unsigned FULL = 0xffffffffu;
 
     float fmn = 0.f, frange = 0.f;
     if (PixTraits<T>::is_float) {
@@ -242,53 +228,54 @@ k_laplacian(const T *__restrict__ img, int64_t pitch, int w, int h, const uint8_
         fmn = mn;
         frange = (mx > mn) ? (float)((double)mx - (double)mn) : 0.f;
     }
-    const int x0 = blockIdx.x * LAP_TW, y0 = blockIdx.y * LAP_TH;
-    for (int i = threadIdx.x; i < PH * PW; i += LAP_THREADS) {
-        int ty = i / PW, tx = i - ty * PW;
-        int gy = kr_reflect101(y0 - R + ty, h), gx = kr_reflect101(x0 - R + tx, w);
-        const T *row = (const T *)((const char *)img + (int64_t)gy * pitch);
-        pix[ty][tx] = (uint8_t)to_u8<T>(row[gx], lut, fmn, frange, invert);
-    }
-    __syncthreads();
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int xs = (blockIdx.x * LAP_WARPS + wid) * VALID;     // first output column of the strip
+    if (xs >= w) return;                                        // whole warp leaves together
+    const int ys = blockIdx.y * LAP_ROWS;
+    const int ye = min(ys + LAP_ROWS, h);
+    const int cx = xs + lane - R;
+    const int col = kr_reflect101(cx, w);
+    const bool store_lane = lane >= R && lane < 32 - R && cx < w;
 
-    if (K <= 3) {
-        for (int i = threadIdx.x; i < LAP_TH * LAP_TW; i += LAP_THREADS) {
-            int ty = i / LAP_TW, tx = i - ty * LAP_TW;
-            int gx = x0 + tx, gy = y0 + ty;
-            if (gx >= w || gy >= h) continue;
+    int vs[NS > 0 ? NS : 1];                  // vertical cascade state
+#pragma unroll
+    for (int i = 0; i < (NS > 0 ? NS : 1); i++) vs[i] = 0;
+    int e_m2 = 0, e_m1 = 0, s_m1 = 0, s_m2 = 0;
+
+    for (int r = ys - R; r < ye + R; r++) {
+        const T *row = (const T *)((const char *)img + (int64_t)kr_reflect101(r, h) * pitch);
+        int v = to_u8<T>(row[col], lut, fmn, frange, invert);
+        // horizontal binomial cascade, alternating direction to stay centred
+#pragma unroll
+        for (int i = 0; i < NS; i++) {
+            int o = (i & 1) ? __shfl_up_sync(FULL, v, 1) : __shfl_down_sync(FULL, v, 1);
+            v += o;
+        }
+        // vertical cascade: after NS stages the value is centred NS/2 rows back
+#pragma unroll
+        for (int i = 0; i < NS; i++) {
+            int t = v + vs[i];
+            vs[i] = v;
+            v = t;
+        }
+        const int s_cur = v;                                  // S at row r - NS/2
+        int e_cur;
+        if (K == 1) e_cur = 0;
+        else e_cur = __shfl_up_sync(FULL, s_cur, 1) + __shfl_down_sync(FULL, s_cur, 1);
+        // output row m = (r - NS/2) - 1 = r - R
+        const int m = r - R;
+        if (m >= ys) {
             int acc;
-            if (K == 1)
-                acc = pix[ty][tx + 1] + pix[ty + 2][tx + 1] + pix[ty + 1][tx] + pix[ty + 1][tx + 2] -
-                      4 * pix[ty + 1][tx + 1];
-            else
-                acc = 2 * (pix[ty][tx] + pix[ty][tx + 2] + pix[ty + 2][tx] + pix[ty + 2][tx + 2]) -
-                      8 * pix[ty + 1][tx + 1];
-            out[(int64_t)gy * out_pitch + gx] = (uint8_t)min(255, max(0, acc));
-        }
-    } else {
-        typedef LapCoef<(K <= 3) ? 5 : K> C;
-        for (int i = threadIdx.x; i < PH * LAP_TW; i += LAP_THREADS) {
-            int ty = i / LAP_TW, tx = i - ty * LAP_TW;
-            int ad = 0, as = 0;
-#pragma unroll
-            for (int j = 0; j < K; j++) {
-                int v = pix[ty][tx + j];
-                ad += C::d2(j) * v;
-                as += C::s(j) * v;
+            if (K == 1) {
+                int e1 = __shfl_up_sync(FULL, s_m1, 1) + __shfl_down_sync(FULL, s_m1, 1);
+                acc = s_m2 + s_cur + e1 - 4 * s_m1;
+            } else {
+                acc = 2 * (e_m2 + e_cur) - 8 * s_m1;
             }
-            rd[ty][tx] = ad;
-            rs[ty][tx] = as;
+            if (store_lane) out[(int64_t)m * out_pitch + cx] = (uint8_t)min(255, max(0, acc));
         }
-        __syncthreads();
-        for (int i = threadIdx.x; i < LAP_TH * LAP_TW; i += LAP_THREADS) {
-            int ty = i / LAP_TW, tx = i - ty * LAP_TW;
-            int gx = x0 + tx, gy = y0 + ty;
-            if (gx >= w || gy >= h) continue;
-            int acc = 0;
-#pragma unroll
-            for (int j = 0; j < K; j++) acc += C::s(j) * rd[ty + j][tx] + C::d2(j) * rs[ty + j][tx];
-            out[(int64_t)gy * out_pitch + gx] = (uint8_t)min(255, max(0, acc));
-        }
+        e_m2 = e_m1; e_m1 = e_cur;
+        s_m2 = s_m1; s_m1 = s_cur;
     }
 }
 
@@ -332,9 +319,11 @@ template <int K, typename T>
 int launch_lap(kr_ctx *ctx, const void *img, int64_t pitch, int w, int h, int slot, int invert,
                uint8_t *out, int64_t out_pitch, cudaStream_t s)
 {
-    dim3 grid((w + LAP_TW - 1) / LAP_TW, (h + LAP_TH - 1) / LAP_TH);
-    k_laplacian<K, T><<<grid, LAP_THREADS, 0, s>>>((const T *)img, pitch, w, h, ctx->d_lut[slot],
-                                                  ctx->d_stats, slot, invert, out, out_pitch);
+    constexpr int R = (K <= 3) ? 1 : K / 2;
+    constexpr int VALID = 32 - 2 * R;
+    dim3 grid((w + LAP_WARPS * VALID - 1) / (LAP_WARPS * VALID), (h + LAP_ROWS - 1) / LAP_ROWS);
+    k_laplacian<K, T><<<grid, LAP_WARPS * 32, 0, s>>>((const T *)img, pitch, w, h, ctx->d_lut[slot],
+                                                     ctx->d_stats, slot, invert, out, out_pitch);
     KR_LAUNCH_CHECK();
     return KR_OK;
 }
