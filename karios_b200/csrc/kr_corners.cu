@@ -16,6 +16,7 @@
 // fixed point (asynchronously, any order) yields exactly the sequential result;
 // truncating the accepted set, in priority order, at maxCorners equals OpenCV's
 // early exit.
+#include <limits.h>
 #include <math.h>
 #include "kr_internal.cuh"
 
@@ -238,6 +239,225 @@ k_eig_candidates(const uint8_t *__restrict__ img, int64_t pitch, const uint8_t *
     if ((tid & 31) == 0 && my_max != KR_ENC_NEG_INF) atomicMax(&s_maxenc, my_max);
     __syncthreads();
     if (tid == 0 && s_maxenc != KR_ENC_NEG_INF) atomicMax(&st->eig_max_enc, s_maxenc);
+}
+
+// ---------------------------------------------------------------------------
+// K3, streaming form (blockSize 15, images >= 16 x 16): no block synchronisation.
+//
+// One warp owns a strip of 128 image columns (4 per lane, one 32-bit load per
+// lane and row) and walks down `seg` rows.  Per row and lane:
+//   Sobel row/column filters from the new pixel row and two rows of history
+//   (neighbour pixels across lanes by warp shuffle) -> 3 products x 4 columns;
+//   vertical 15-row sums are running float64 sums per column (add the new
+//   product row, subtract the one 15 rows back, kept as float32 in a per-warp
+//   shared-memory ring); horizontal 15-column sums combine per-lane prefix /
+//   suffix sums of the 4 columns with those of lanes l-2 .. l+2 (float64
+//   shuffles); eigenvalue; 3x3 local maximum against two rows of history;
+//   candidates are buffered per warp and appended with one atomic per flush.
+// Out-of-image rows / columns of the box filter are REFLECT_101 of the product
+// plane: the stream simply visits the reflected row / column with the roles of
+// the two neighbours swapped, which reproduces the product AT the reflected
+// position.  float64 sums of these float32 products are exact in all but
+// ~1e-7 of the pixels, so the summation order is free.
+constexpr int EC_WARPS = 8, EC_OUTW = 104, EC_LEFT = 12, EC_CBUF = 96;
+
+__device__ __forceinline__ float eig_from_sums(double sxx, double sxy, double syy)
+{
+    float a = __fmul_rn((float)sxx, 0.5f), b = (float)sxy, c = __fmul_rn((float)syy, 0.5f);
+    float t = __fsub_rn(a, c);
+    return __fsub_rn(__fadd_rn(a, c), __fsqrt_rn(__fadd_rn(__fmul_rn(t, t), __fmul_rn(b, b))));
+}
+
+template <bool ALIGNED>
+__global__ void __launch_bounds__(EC_WARPS * 32, 1)
+k_eig_stream(const uint8_t *__restrict__ img, int64_t pitch, const uint8_t *__restrict__ mask,
+             int64_t mpitch, int w, int h, float s, int tail_start, float *__restrict__ eig_out,
+             int64_t eig_pitch, uint64_t *__restrict__ cand, uint32_t cand_cap, KrDevStats *st, int emit,
+             int seg)
+{
+    constexpr unsigned FULL = 0xffffffffu;
+    extern __shared__ __align__(16) unsigned char ec_smem[];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    float4 *ring = reinterpret_cast<float4 *>(ec_smem) + (size_t)wid * 16 * 3 * 32;   // [16][3][32] float4
+    uint64_t *cbuf = reinterpret_cast<uint64_t *>(ec_smem + (size_t)EC_WARPS * 16 * 3 * 32 * 16) +
+                     (size_t)wid * EC_CBUF;
+
+    const int xs = (blockIdx.x * EC_WARPS + wid) * EC_OUTW;        // first output column
+    if (xs >= w) return;
+    const int ys = blockIdx.y * seg, ye = min(ys + seg, h);
+    const int xb = xs - EC_LEFT + 4 * lane;                        // first (virtual) column of the lane
+    const bool interior = ALIGNED && (xs - EC_LEFT >= 0) && (xs - EC_LEFT + 128 <= w);
+    const float s2 = 2.0f * s;
+
+    int tc[4];                 // true column of each virtual column
+    bool crefl[4], ctail[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        int vx = xb + j;
+        tc[j] = kr_reflect101(vx, w);
+        crefl[j] = vx < 0 || vx >= w;
+        ctail[j] = tc[j] >= tail_start;
+    }
+    const bool out_lane = lane >= 3 && lane <= 28;
+
+    int R1[4] = {0, 0, 0, 0}, R2[4] = {0, 0, 0, 0};        // row r-1, r-2
+    float T1[4] = {0, 0, 0, 0}, T2[4] = {0, 0, 0, 0};
+    double cs[3][4];
+#pragma unroll
+    for (int c = 0; c < 3; c++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) cs[c][j] = 0.0;
+    float E1[6] = {0, 0, 0, 0, 0, 0}, E2[6] = {0, 0, 0, 0, 0, 0};   // eig rows q-1, q-2: [L, 0..3, R]
+    uint32_t my_max = KR_ENC_NEG_INF;
+    int ccount = 0;                                                    // warp-uniform
+    int nprod = 0;
+
+    for (int r = ys - 9; r <= ye + 8; r++) {
+        // ---- pixel row r (virtual) -> row filters ---------------------------
+        const int tr = kr_reflect101(r, h);
+        const uint8_t *prow = img + (int64_t)tr * pitch;
+        uint32_t pk;
+        if (interior) {
+            pk = __ldg(reinterpret_cast<const uint32_t *>(prow + xb));
+        } else {
+            pk = (uint32_t)__ldg(prow + tc[0]) | ((uint32_t)__ldg(prow + tc[1]) << 8) |
+                 ((uint32_t)__ldg(prow + tc[2]) << 16) | ((uint32_t)__ldg(prow + tc[3]) << 24);
+        }
+        const uint32_t wl = __shfl_up_sync(FULL, pk, 1), wr = __shfl_down_sync(FULL, pk, 1);
+        int q[6];
+        q[0] = (int)(wl >> 24);
+        q[1] = (int)(pk & 255u); q[2] = (int)((pk >> 8) & 255u); q[3] = (int)((pk >> 16) & 255u);
+        q[4] = (int)(pk >> 24);
+        q[5] = (int)(wr & 255u);
+        int R0[4];
+        float T0[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            int a = q[j], c = q[j + 2];                     // p[x-1], p[x+1] in virtual order
+            if (crefl[j]) { int t = a; a = c; c = t; }       // reflected column: true neighbours swap
+            const float fa = (float)a, fb = (float)q[j + 1], fc = (float)c;
+            R0[j] = c - a;
+            if (!ctail[j])
+                T0[j] = __fmaf_rn(s, fc, __fmaf_rn(s2, fb, __fmul_rn(s, fa)));
+            else
+                T0[j] = __fadd_rn(__fadd_rn(__fmul_rn(s, fa), __fmul_rn(s2, fb)), __fmul_rn(s, fc));
+        }
+        const int t = r - (ys - 9);
+        if (t >= 2) {
+            // ---- products of (virtual) row r-1 ------------------------------
+            const bool rrefl = (r - 1) < 0 || (r - 1) >= h;
+            float px[3][4];
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                float dx = __fmaf_rn(s, (float)(R2[j] + R0[j]), __fmul_rn(s2, (float)R1[j]));
+                float dy = rrefl ? __fsub_rn(T2[j], T0[j]) : __fsub_rn(T0[j], T2[j]);
+                px[0][j] = __fmul_rn(dx, dx);
+                px[1][j] = __fmul_rn(dx, dy);
+                px[2][j] = __fmul_rn(dy, dy);
+            }
+            // ---- vertical running sums (float64), ring of float32 products ---
+            nprod++;
+            const int rd_slot = r & 15, wr_slot = (r - 1) & 15;
+#pragma unroll
+            for (int c = 0; c < 3; c++) {
+                if (nprod > 15) {
+                    float4 o = ring[(rd_slot * 3 + c) * 32 + lane];
+                    cs[c][0] -= (double)o.x; cs[c][1] -= (double)o.y;
+                    cs[c][2] -= (double)o.z; cs[c][3] -= (double)o.w;
+                }
+                cs[c][0] += (double)px[c][0]; cs[c][1] += (double)px[c][1];
+                cs[c][2] += (double)px[c][2]; cs[c][3] += (double)px[c][3];
+                ring[(wr_slot * 3 + c) * 32 + lane] = make_float4(px[c][0], px[c][1], px[c][2], px[c][3]);
+            }
+            if (nprod >= 15) {
+                // ---- horizontal 15-column sums -> eigenvalue row qy = r - 8 ---
+                double bx[3][4];
+#pragma unroll
+                for (int c = 0; c < 3; c++) {
+                    const double c0 = cs[c][0], c1 = cs[c][1], c2 = cs[c][2], c3 = cs[c][3];
+                    const double P2 = c0 + c1, P3 = P2 + c2, qq = P3 + c3;
+                    const double S2 = c2 + c3, S3 = S2 + c1;
+                    const double mid = __shfl_up_sync(FULL, qq, 1) + qq + __shfl_down_sync(FULL, qq, 1);
+                    const double a3 = __shfl_up_sync(FULL, S3, 2), a2 = __shfl_up_sync(FULL, S2, 2),
+                                 a1 = __shfl_up_sync(FULL, c3, 2);
+                    const double b1 = __shfl_down_sync(FULL, c0, 2), b2 = __shfl_down_sync(FULL, P2, 2),
+                                 b3 = __shfl_down_sync(FULL, P3, 2);
+                    bx[c][0] = mid + a3;
+                    bx[c][1] = (mid + a2) + b1;
+                    bx[c][2] = (mid + a1) + b2;
+                    bx[c][3] = mid + b3;
+                }
+                float E0[6];
+#pragma unroll
+                for (int j = 0; j < 4; j++) E0[j + 1] = eig_from_sums(bx[0][j], bx[1][j], bx[2][j]);
+                E0[0] = __shfl_up_sync(FULL, E0[4], 1);
+                E0[5] = __shfl_down_sync(FULL, E0[1], 1);
+                // ---- 3x3 local maxima of row m = r - 9 ------------------------
+                const int m = r - 9;
+                if (m >= ys && m < ye) {                       // warp-uniform
+                    uint32_t mk = 0x01010101u;
+                    if (mask) {
+                        const uint8_t *mrow = mask + (int64_t)m * mpitch;
+                        mk = 0;
+#pragma unroll
+                        for (int j = 0; j < 4; j++) {
+                            int x = xb + j;
+                            if (x >= 0 && x < w && __ldg(mrow + x)) mk |= 1u << (8 * j);
+                        }
+                    }
+#pragma unroll
+                    for (int j = 0; j < 4; j++) {
+                        const int x = xb + j;
+                        const float v = E1[j + 1];
+                        const bool inimg = out_lane && x < w;          // x >= 0 for output lanes
+                        const bool mok = (mk >> (8 * j)) & 1u;
+                        if (inimg) {
+                            if (eig_out) *(float *)((char *)eig_out + (int64_t)m * eig_pitch + (int64_t)x * 4) = v;
+                            if (mok) my_max = max(my_max, kr_f32_enc(v));
+                        }
+                        bool is_c = emit && inimg && mok && v > 0.f && x >= 1 && x <= w - 2 && m >= 1 && m <= h - 2;
+                        if (is_c)
+                            is_c = v >= E2[j] && v >= E2[j + 1] && v >= E2[j + 2] && v >= E1[j] &&
+                                   v >= E1[j + 2] && v >= E0[j] && v >= E0[j + 1] && v >= E0[j + 2];
+                        const unsigned bal = __ballot_sync(FULL, is_c);
+                        if (bal) {
+                            if (ccount > EC_CBUF - 32) {               // flush the warp buffer
+                                uint32_t base = 0;
+                                if (lane == 0) base = atomicAdd(&st->n_cand, (uint32_t)ccount);
+                                base = __shfl_sync(FULL, base, 0);
+                                __syncwarp();
+                                for (int k = lane; k < ccount; k += 32) {
+                                    if (base + k < cand_cap) cand[base + k] = cbuf[k]; else st->overflow = 1;
+                                }
+                                __syncwarp();
+                                ccount = 0;
+                            }
+                            if (is_c)
+                                cbuf[ccount + __popc(bal & ((1u << lane) - 1))] =
+                                    ((uint64_t)__float_as_uint(v) << 32) | (uint32_t)(m * w + x);
+                            ccount += __popc(bal);
+                        }
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < 6; j++) { E2[j] = E1[j]; E1[j] = E0[j]; }
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; j++) { R2[j] = R1[j]; R1[j] = R0[j]; T2[j] = T1[j]; T1[j] = T0[j]; }
+    }
+    // final flush, masked maximum
+    __syncwarp();
+    if (ccount > 0) {
+        uint32_t base = 0;
+        if (lane == 0) base = atomicAdd(&st->n_cand, (uint32_t)ccount);
+        base = __shfl_sync(FULL, base, 0);
+        for (int k = lane; k < ccount; k += 32) {
+            if (base + k < cand_cap) cand[base + k] = cbuf[k]; else st->overflow = 1;
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) my_max = max(my_max, __shfl_xor_sync(FULL, my_max, o));
+    if (lane == 0 && my_max != KR_ENC_NEG_INF) atomicMax(&st->eig_max_enc, my_max);
 }
 
 // threshold = float(maxVal * qualityLevel) (cv::threshold takes a double and
@@ -534,10 +754,47 @@ int krl_good_features(kr_ctx *ctx, const uint8_t *img, int64_t pitch, const uint
 
     k_clear_counts<<<1, 1, 0, s>>>(ctx->d_stats);
     KR_LAUNCH_CHECK();
-    dim3 grid((w + EG_TW - 1) / EG_TW, (h + EG_TH - 1) / EG_TH);
-    k_eig_candidates<<<grid, EG_THREADS, smem, s>>>(img, pitch, mask, mask_pitch, w, h, block, scale,
-                                                   tail_start, eig_out, eig_pitch, ctx->d_cand,
-                                                   (uint32_t)ctx->cand_cap, ctx->d_stats, emit);
+    if (block == 15 && w >= 16 && h >= 16) {
+        const size_t esm = (size_t)EC_WARPS * (16 * 3 * 32 * 16 + EC_CBUF * 8);
+        static bool ec_set = false;
+        if (!ec_set) {
+            KR_CUDA(cudaFuncSetAttribute(k_eig_stream<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)esm));
+            KR_CUDA(cudaFuncSetAttribute(k_eig_stream<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)esm));
+            ec_set = true;
+        }
+        const bool aligned = ((uintptr_t)img % 4 == 0) && (pitch % 4 == 0);
+        // rows per warp: whole waves of co-resident blocks (1 block per SM), each
+        // segment pays 18 warm-up rows -- pick the cheaper of two wave counts
+        const int sb = (w + EC_WARPS * EC_OUTW - 1) / (EC_WARPS * EC_OUTW);
+        int best_seg = h, best_cost = INT_MAX;
+        const int w0 = (int)(((int64_t)sb * ((h + 255) / 256) + ctx->num_sms - 1) / ctx->num_sms);
+        for (int waves = (w0 > 1 ? w0 - 1 : 1); waves <= w0 + 1; waves++) {
+            int segs = waves * ctx->num_sms / sb;
+            if (segs < 1) segs = 1;
+            int sg = (h + segs - 1) / segs;
+            if (sg < 32) sg = 32;
+            int nseg = (h + sg - 1) / sg;
+            int wv = (sb * nseg + ctx->num_sms - 1) / ctx->num_sms;
+            int cost = wv * (sg + 18);
+            if (cost < best_cost) { best_cost = cost; best_seg = sg; }
+        }
+        const int seg = best_seg;
+        dim3 grid(sb, (h + seg - 1) / seg);
+        if (aligned)
+            k_eig_stream<true><<<grid, EC_WARPS * 32, esm, s>>>(img, pitch, mask, mask_pitch, w, h, scale,
+                                                               tail_start, eig_out, eig_pitch, ctx->d_cand,
+                                                               (uint32_t)ctx->cand_cap, ctx->d_stats, emit, seg);
+        else
+            k_eig_stream<false><<<grid, EC_WARPS * 32, esm, s>>>(img, pitch, mask, mask_pitch, w, h, scale,
+                                                                tail_start, eig_out, eig_pitch, ctx->d_cand,
+                                                                (uint32_t)ctx->cand_cap, ctx->d_stats, emit, seg);
+    } else {
+        // generic tile kernel: any blockSize <= 31, any image size
+        dim3 grid((w + EG_TW - 1) / EG_TW, (h + EG_TH - 1) / EG_TH);
+        k_eig_candidates<<<grid, EG_THREADS, smem, s>>>(img, pitch, mask, mask_pitch, w, h, block, scale,
+                                                       tail_start, eig_out, eig_pitch, ctx->d_cand,
+                                                       (uint32_t)ctx->cand_cap, ctx->d_stats, emit);
+    }
     KR_LAUNCH_CHECK();
     KR_MARK(ctx, 4, s);
     if (!emit) return KR_OK;

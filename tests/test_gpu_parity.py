@@ -109,7 +109,8 @@ def test_min_eigen_val(golden, N, ctx, name):
 
 def test_min_eigen_val_small_images(N, ctx):
     rng = np.random.default_rng(9)
-    for shape in ((1, 1), (2, 3), (5, 5), (9, 40), (33, 65), (64, 32)):
+    for shape in ((1, 1), (2, 3), (5, 5), (9, 40), (33, 65), (64, 32), (16, 16), (17, 130), (300, 1301),
+                  (530, 212)):
         a = rng.integers(0, 255, shape).astype(np.uint8)
         for block in (3, 15):
             e = ctx.corner_min_eigen_val(dev(a), block).cpu().numpy()
