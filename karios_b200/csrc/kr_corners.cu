@@ -259,7 +259,7 @@ k_eig_candidates(const uint8_t *__restrict__ img, int64_t pitch, const uint8_t *
 // the two neighbours swapped, which reproduces the product AT the reflected
 // position.  float64 sums of these float32 products are exact in all but
 // ~1e-7 of the pixels, so the summation order is free.
-constexpr int EC_WARPS = 8, EC_OUTW = 104, EC_LEFT = 12, EC_CBUF = 96;
+constexpr int EC_WARPS = 8, EC_OUTW = 104, EC_LEFT = 12, EC_CBUF = 256;
 
 __device__ __forceinline__ float eig_from_sums(double sxx, double sxy, double syy)
 {
@@ -268,39 +268,52 @@ __device__ __forceinline__ float eig_from_sums(double sxx, double sxy, double sy
     return __fsub_rn(__fadd_rn(a, c), __fsqrt_rn(__fadd_rn(__fmul_rn(t, t), __fmul_rn(b, b))));
 }
 
-template <bool ALIGNED>
-__global__ void __launch_bounds__(EC_WARPS * 32, 1)
-k_eig_stream(const uint8_t *__restrict__ img, int64_t pitch, const uint8_t *__restrict__ mask,
-             int64_t mpitch, int w, int h, float s, int tail_start, float *__restrict__ eig_out,
-             int64_t eig_pitch, uint64_t *__restrict__ cand, uint32_t cand_cap, KrDevStats *st, int emit,
-             int seg)
+// BORDER = the strip touches the left / right image border, the SIMD-tail columns
+// or unaligned planes: per-column reflection, tail rounding and bounds checks.
+// Interior strips (the vast majority) take the lean path.
+template <bool BORDER, bool HAS_MASK, bool DEBUG_EIG>
+__device__ __forceinline__ void eig_stream_body(
+    const uint8_t *__restrict__ img, int64_t pitch, const uint8_t *__restrict__ mask, int64_t mpitch,
+    int w, int h, float s, int tail_start, float *__restrict__ eig_out, int64_t eig_pitch,
+    uint64_t *__restrict__ cand, uint32_t cand_cap, KrDevStats *st, int emit, int xs, int ys, int ye,
+    float4 *ring, uint64_t *cbuf, int lane)
 {
     constexpr unsigned FULL = 0xffffffffu;
-    extern __shared__ __align__(16) unsigned char ec_smem[];
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    float4 *ring = reinterpret_cast<float4 *>(ec_smem) + (size_t)wid * 16 * 3 * 32;   // [16][3][32] float4
-    uint64_t *cbuf = reinterpret_cast<uint64_t *>(ec_smem + (size_t)EC_WARPS * 16 * 3 * 32 * 16) +
-                     (size_t)wid * EC_CBUF;
-
-    const int xs = (blockIdx.x * EC_WARPS + wid) * EC_OUTW;        // first output column
-    if (xs >= w) return;
-    const int ys = blockIdx.y * seg, ye = min(ys + seg, h);
     const int xb = xs - EC_LEFT + 4 * lane;                        // first (virtual) column of the lane
-    const bool interior = ALIGNED && (xs - EC_LEFT >= 0) && (xs - EC_LEFT + 128 <= w);
     const float s2 = 2.0f * s;
-
-    int tc[4];                 // true column of each virtual column
+    int tc[4];
     bool crefl[4], ctail[4];
 #pragma unroll
     for (int j = 0; j < 4; j++) {
-        int vx = xb + j;
-        tc[j] = kr_reflect101(vx, w);
-        crefl[j] = vx < 0 || vx >= w;
-        ctail[j] = tc[j] >= tail_start;
+        const int vx = xb + j;
+        tc[j] = BORDER ? kr_reflect101(vx, w) : vx;
+        crefl[j] = BORDER && (vx < 0 || vx >= w);
+        ctail[j] = BORDER && (tc[j] >= tail_start);
     }
     const bool out_lane = lane >= 3 && lane <= 28;
 
-    int R1[4] = {0, 0, 0, 0}, R2[4] = {0, 0, 0, 0};        // row r-1, r-2
+    auto load_row = [&](int r) -> uint32_t {
+        const int tr = (r < 0) ? -r : ((r >= h) ? 2 * (h - 1) - r : r);     // single reflection (h >= 16)
+        const uint8_t *prow = img + (int64_t)tr * pitch;
+        if (!BORDER) return __ldg(reinterpret_cast<const uint32_t *>(prow + xb));
+        return (uint32_t)__ldg(prow + tc[0]) | ((uint32_t)__ldg(prow + tc[1]) << 8) |
+               ((uint32_t)__ldg(prow + tc[2]) << 16) | ((uint32_t)__ldg(prow + tc[3]) << 24);
+    };
+    auto load_mask = [&](int m) -> uint32_t {                                // 1 byte per column
+        if (!HAS_MASK) return 0x01010101u;
+        if (m < 0 || m >= h) return 0u;
+        const uint8_t *mrow = mask + (int64_t)m * mpitch;
+        if (!BORDER) return __ldg(reinterpret_cast<const uint32_t *>(mrow + xb));
+        uint32_t mk = 0;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const int x = xb + j;
+            if (x >= 0 && x < w) mk |= (uint32_t)__ldg(mrow + x) << (8 * j);
+        }
+        return mk;
+    };
+
+    int R1[4] = {0, 0, 0, 0}, R2[4] = {0, 0, 0, 0};        // rows r-1, r-2
     float T1[4] = {0, 0, 0, 0}, T2[4] = {0, 0, 0, 0};
     double cs[3][4];
 #pragma unroll
@@ -312,45 +325,51 @@ k_eig_stream(const uint8_t *__restrict__ img, int64_t pitch, const uint8_t *__re
     int ccount = 0;                                                    // warp-uniform
     int nprod = 0;
 
-    for (int r = ys - 9; r <= ye + 8; r++) {
-        // ---- pixel row r (virtual) -> row filters ---------------------------
-        const int tr = kr_reflect101(r, h);
-        const uint8_t *prow = img + (int64_t)tr * pitch;
-        uint32_t pk;
-        if (interior) {
-            pk = __ldg(reinterpret_cast<const uint32_t *>(prow + xb));
-        } else {
-            pk = (uint32_t)__ldg(prow + tc[0]) | ((uint32_t)__ldg(prow + tc[1]) << 8) |
-                 ((uint32_t)__ldg(prow + tc[2]) << 16) | ((uint32_t)__ldg(prow + tc[3]) << 24);
+    const int r_first = ys - 9, r_last = ye + 8;
+    uint32_t pk_next = load_row(r_first);
+    uint32_t mk_next = load_mask(r_first - 9);
+    for (int r = r_first; r <= r_last; r++) {
+        const uint32_t pk = pk_next;
+        const uint32_t mk = mk_next;
+        if (r < r_last) {                       // prefetch the next pixel / mask words
+            pk_next = load_row(r + 1);
+            mk_next = load_mask(r + 1 - 9);
         }
+        // ---- pixel row r (virtual) -> row filters ---------------------------
         const uint32_t wl = __shfl_up_sync(FULL, pk, 1), wr = __shfl_down_sync(FULL, pk, 1);
         int q[6];
         q[0] = (int)(wl >> 24);
         q[1] = (int)(pk & 255u); q[2] = (int)((pk >> 8) & 255u); q[3] = (int)((pk >> 16) & 255u);
         q[4] = (int)(pk >> 24);
         q[5] = (int)(wr & 255u);
+        float fq[6];
+#pragma unroll
+        for (int j = 0; j < 6; j++) fq[j] = (float)q[j];
         int R0[4];
         float T0[4];
 #pragma unroll
         for (int j = 0; j < 4; j++) {
-            int a = q[j], c = q[j + 2];                     // p[x-1], p[x+1] in virtual order
-            if (crefl[j]) { int t = a; a = c; c = t; }       // reflected column: true neighbours swap
-            const float fa = (float)a, fb = (float)q[j + 1], fc = (float)c;
-            R0[j] = c - a;
-            if (!ctail[j])
-                T0[j] = __fmaf_rn(s, fc, __fmaf_rn(s2, fb, __fmul_rn(s, fa)));
+            int ia = q[j], ic = q[j + 2];                    // p[x-1], p[x+1] in virtual order
+            float fa = fq[j], fc = fq[j + 2];
+            if (BORDER && crefl[j]) {                        // reflected column: true neighbours swap
+                int ti = ia; ia = ic; ic = ti;
+                float tf = fa; fa = fc; fc = tf;
+            }
+            R0[j] = ic - ia;
+            if (BORDER && ctail[j])
+                T0[j] = __fadd_rn(__fadd_rn(__fmul_rn(s, fa), __fmul_rn(s2, fq[j + 1])), __fmul_rn(s, fc));
             else
-                T0[j] = __fadd_rn(__fadd_rn(__fmul_rn(s, fa), __fmul_rn(s2, fb)), __fmul_rn(s, fc));
+                T0[j] = __fmaf_rn(s, fc, __fmaf_rn(s2, fq[j + 1], __fmul_rn(s, fa)));
         }
-        const int t = r - (ys - 9);
-        if (t >= 2) {
+        if (r >= r_first + 2) {
             // ---- products of (virtual) row r-1 ------------------------------
             const bool rrefl = (r - 1) < 0 || (r - 1) >= h;
             float px[3][4];
 #pragma unroll
             for (int j = 0; j < 4; j++) {
-                float dx = __fmaf_rn(s, (float)(R2[j] + R0[j]), __fmul_rn(s2, (float)R1[j]));
-                float dy = rrefl ? __fsub_rn(T2[j], T0[j]) : __fsub_rn(T0[j], T2[j]);
+                const float dx = __fmaf_rn(s, (float)(R2[j] + R0[j]), __fmul_rn(s2, (float)R1[j]));
+                const float d0 = __fsub_rn(T0[j], T2[j]);
+                const float dy = rrefl ? -d0 : d0;           // exact negation
                 px[0][j] = __fmul_rn(dx, dx);
                 px[1][j] = __fmul_rn(dx, dy);
                 px[2][j] = __fmul_rn(dy, dy);
@@ -358,83 +377,84 @@ k_eig_stream(const uint8_t *__restrict__ img, int64_t pitch, const uint8_t *__re
             // ---- vertical running sums (float64), ring of float32 products ---
             nprod++;
             const int rd_slot = r & 15, wr_slot = (r - 1) & 15;
+            if (nprod > 15) {
 #pragma unroll
-            for (int c = 0; c < 3; c++) {
-                if (nprod > 15) {
-                    float4 o = ring[(rd_slot * 3 + c) * 32 + lane];
+                for (int c = 0; c < 3; c++) {
+                    const float4 o = ring[(rd_slot * 3 + c) * 32];
                     cs[c][0] -= (double)o.x; cs[c][1] -= (double)o.y;
                     cs[c][2] -= (double)o.z; cs[c][3] -= (double)o.w;
                 }
+            }
+#pragma unroll
+            for (int c = 0; c < 3; c++) {
                 cs[c][0] += (double)px[c][0]; cs[c][1] += (double)px[c][1];
                 cs[c][2] += (double)px[c][2]; cs[c][3] += (double)px[c][3];
-                ring[(wr_slot * 3 + c) * 32 + lane] = make_float4(px[c][0], px[c][1], px[c][2], px[c][3]);
+                ring[(wr_slot * 3 + c) * 32] = make_float4(px[c][0], px[c][1], px[c][2], px[c][3]);
             }
             if (nprod >= 15) {
-                // ---- horizontal 15-column sums -> eigenvalue row qy = r - 8 ---
-                double bx[3][4];
-#pragma unroll
-                for (int c = 0; c < 3; c++) {
-                    const double c0 = cs[c][0], c1 = cs[c][1], c2 = cs[c][2], c3 = cs[c][3];
-                    const double P2 = c0 + c1, P3 = P2 + c2, qq = P3 + c3;
-                    const double S2 = c2 + c3, S3 = S2 + c1;
-                    const double mid = __shfl_up_sync(FULL, qq, 1) + qq + __shfl_down_sync(FULL, qq, 1);
-                    const double a3 = __shfl_up_sync(FULL, S3, 2), a2 = __shfl_up_sync(FULL, S2, 2),
-                                 a1 = __shfl_up_sync(FULL, c3, 2);
-                    const double b1 = __shfl_down_sync(FULL, c0, 2), b2 = __shfl_down_sync(FULL, P2, 2),
-                                 b3 = __shfl_down_sync(FULL, P3, 2);
-                    bx[c][0] = mid + a3;
-                    bx[c][1] = (mid + a2) + b1;
-                    bx[c][2] = (mid + a1) + b2;
-                    bx[c][3] = mid + b3;
-                }
+                // ---- horizontal 15-column sums -> eigenvalue row r - 8 --------
                 float E0[6];
+                {
+                    double bx[3][4];
 #pragma unroll
-                for (int j = 0; j < 4; j++) E0[j + 1] = eig_from_sums(bx[0][j], bx[1][j], bx[2][j]);
+                    for (int c = 0; c < 3; c++) {
+                        const double c0 = cs[c][0], c1 = cs[c][1], c2 = cs[c][2], c3 = cs[c][3];
+                        const double P2 = c0 + c1, P3 = P2 + c2, qq = P3 + c3;
+                        const double S2 = c2 + c3, S3 = S2 + c1;
+                        const double mid = __shfl_up_sync(FULL, qq, 1) + qq + __shfl_down_sync(FULL, qq, 1);
+                        const double a3 = __shfl_up_sync(FULL, S3, 2), a2 = __shfl_up_sync(FULL, S2, 2),
+                                     a1 = __shfl_up_sync(FULL, c3, 2);
+                        const double b1 = __shfl_down_sync(FULL, c0, 2), b2 = __shfl_down_sync(FULL, P2, 2),
+                                     b3 = __shfl_down_sync(FULL, P3, 2);
+                        bx[c][0] = mid + a3;
+                        bx[c][1] = (mid + a2) + b1;
+                        bx[c][2] = (mid + a1) + b2;
+                        bx[c][3] = mid + b3;
+                    }
+#pragma unroll
+                    for (int j = 0; j < 4; j++) E0[j + 1] = eig_from_sums(bx[0][j], bx[1][j], bx[2][j]);
+                }
                 E0[0] = __shfl_up_sync(FULL, E0[4], 1);
                 E0[5] = __shfl_down_sync(FULL, E0[1], 1);
                 // ---- 3x3 local maxima of row m = r - 9 ------------------------
                 const int m = r - 9;
                 if (m >= ys && m < ye) {                       // warp-uniform
-                    uint32_t mk = 0x01010101u;
-                    if (mask) {
-                        const uint8_t *mrow = mask + (int64_t)m * mpitch;
-                        mk = 0;
-#pragma unroll
-                        for (int j = 0; j < 4; j++) {
-                            int x = xb + j;
-                            if (x >= 0 && x < w && __ldg(mrow + x)) mk |= 1u << (8 * j);
-                        }
-                    }
+                    const bool row_ok = emit && m >= 1 && m <= h - 2;
+                    unsigned cm = 0;                            // candidate bits of the 4 columns
 #pragma unroll
                     for (int j = 0; j < 4; j++) {
                         const int x = xb + j;
                         const float v = E1[j + 1];
-                        const bool inimg = out_lane && x < w;          // x >= 0 for output lanes
-                        const bool mok = (mk >> (8 * j)) & 1u;
+                        const bool inimg = out_lane && (!BORDER || x < w);
+                        const bool mok = !HAS_MASK || ((mk >> (8 * j)) & 255u) != 0;
                         if (inimg) {
-                            if (eig_out) *(float *)((char *)eig_out + (int64_t)m * eig_pitch + (int64_t)x * 4) = v;
+                            if (DEBUG_EIG) *(float *)((char *)eig_out + (int64_t)m * eig_pitch + (int64_t)x * 4) = v;
                             if (mok) my_max = max(my_max, kr_f32_enc(v));
                         }
-                        bool is_c = emit && inimg && mok && v > 0.f && x >= 1 && x <= w - 2 && m >= 1 && m <= h - 2;
-                        if (is_c)
-                            is_c = v >= E2[j] && v >= E2[j + 1] && v >= E2[j + 2] && v >= E1[j] &&
-                                   v >= E1[j + 2] && v >= E0[j] && v >= E0[j + 1] && v >= E0[j + 2];
-                        const unsigned bal = __ballot_sync(FULL, is_c);
-                        if (bal) {
-                            if (ccount > EC_CBUF - 32) {               // flush the warp buffer
-                                uint32_t base = 0;
-                                if (lane == 0) base = atomicAdd(&st->n_cand, (uint32_t)ccount);
-                                base = __shfl_sync(FULL, base, 0);
-                                __syncwarp();
-                                for (int k = lane; k < ccount; k += 32) {
-                                    if (base + k < cand_cap) cand[base + k] = cbuf[k]; else st->overflow = 1;
-                                }
-                                __syncwarp();
-                                ccount = 0;
+                        bool is_c = row_ok && inimg && mok && v > 0.f && (!BORDER || (x >= 1 && x <= w - 2));
+                        is_c = is_c && v >= E2[j] && v >= E2[j + 1] && v >= E2[j + 2] && v >= E1[j] &&
+                               v >= E1[j + 2] && v >= E0[j] && v >= E0[j + 1] && v >= E0[j + 2];
+                        if (is_c) cm |= 1u << j;
+                    }
+                    if (__any_sync(FULL, cm != 0)) {
+                        if (ccount > EC_CBUF - 128) {              // flush the warp buffer
+                            uint32_t base = 0;
+                            if (lane == 0) base = atomicAdd(&st->n_cand, (uint32_t)ccount);
+                            base = __shfl_sync(FULL, base, 0);
+                            __syncwarp();
+                            for (int k = lane; k < ccount; k += 32) {
+                                if (base + k < cand_cap) cand[base + k] = cbuf[k]; else st->overflow = 1;
                             }
+                            __syncwarp();
+                            ccount = 0;
+                        }
+#pragma unroll
+                        for (int j = 0; j < 4; j++) {
+                            const bool is_c = (cm >> j) & 1u;
+                            const unsigned bal = __ballot_sync(FULL, is_c);
                             if (is_c)
                                 cbuf[ccount + __popc(bal & ((1u << lane) - 1))] =
-                                    ((uint64_t)__float_as_uint(v) << 32) | (uint32_t)(m * w + x);
+                                    ((uint64_t)__float_as_uint(E1[j + 1]) << 32) | (uint32_t)(m * w + xb + j);
                             ccount += __popc(bal);
                         }
                     }
@@ -458,6 +478,34 @@ k_eig_stream(const uint8_t *__restrict__ img, int64_t pitch, const uint8_t *__re
     }
     for (int o = 16; o > 0; o >>= 1) my_max = max(my_max, __shfl_xor_sync(FULL, my_max, o));
     if (lane == 0 && my_max != KR_ENC_NEG_INF) atomicMax(&st->eig_max_enc, my_max);
+}
+
+template <bool HAS_MASK, bool DEBUG_EIG>
+__global__ void __launch_bounds__(EC_WARPS * 32, 1)
+k_eig_stream(const uint8_t *__restrict__ img, int64_t pitch, const uint8_t *__restrict__ mask,
+             int64_t mpitch, int w, int h, float s, int tail_start, float *__restrict__ eig_out,
+             int64_t eig_pitch, uint64_t *__restrict__ cand, uint32_t cand_cap, KrDevStats *st, int emit,
+             int seg, int aligned)
+{
+    extern __shared__ __align__(16) unsigned char ec_smem[];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    float4 *ring = reinterpret_cast<float4 *>(ec_smem) + (size_t)wid * 16 * 3 * 32 + lane;   // [16][3][32]
+    uint64_t *cbuf = reinterpret_cast<uint64_t *>(ec_smem + (size_t)EC_WARPS * 16 * 3 * 32 * 16) +
+                     (size_t)wid * EC_CBUF;
+    const int xs = (blockIdx.x * EC_WARPS + wid) * EC_OUTW;        // first output column
+    if (xs >= w) return;
+    const int ys = blockIdx.y * seg, ye = min(ys + seg, h);
+    // lean path: all 128 columns inside the image, none in the SIMD tail, aligned planes
+    const bool interior = aligned && (xs - EC_LEFT >= 0) && (xs - EC_LEFT + 128 <= w) &&
+                          (xs - EC_LEFT + 128 <= tail_start);
+    if (interior)
+        eig_stream_body<false, HAS_MASK, DEBUG_EIG>(img, pitch, mask, mpitch, w, h, s, tail_start, eig_out,
+                                                    eig_pitch, cand, cand_cap, st, emit, xs, ys, ye, ring,
+                                                    cbuf, lane);
+    else
+        eig_stream_body<true, HAS_MASK, DEBUG_EIG>(img, pitch, mask, mpitch, w, h, s, tail_start, eig_out,
+                                                   eig_pitch, cand, cand_cap, st, emit, xs, ys, ye, ring,
+                                                   cbuf, lane);
 }
 
 // threshold = float(maxVal * qualityLevel) (cv::threshold takes a double and
@@ -758,11 +806,14 @@ int krl_good_features(kr_ctx *ctx, const uint8_t *img, int64_t pitch, const uint
         const size_t esm = (size_t)EC_WARPS * (16 * 3 * 32 * 16 + EC_CBUF * 8);
         static bool ec_set = false;
         if (!ec_set) {
-            KR_CUDA(cudaFuncSetAttribute(k_eig_stream<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)esm));
-            KR_CUDA(cudaFuncSetAttribute(k_eig_stream<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)esm));
+            KR_CUDA(cudaFuncSetAttribute(k_eig_stream<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)esm));
+            KR_CUDA(cudaFuncSetAttribute(k_eig_stream<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)esm));
+            KR_CUDA(cudaFuncSetAttribute(k_eig_stream<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)esm));
+            KR_CUDA(cudaFuncSetAttribute(k_eig_stream<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)esm));
             ec_set = true;
         }
-        const bool aligned = ((uintptr_t)img % 4 == 0) && (pitch % 4 == 0);
+        int aligned = ((uintptr_t)img % 4 == 0) && (pitch % 4 == 0);
+        if (mask) aligned = aligned && ((uintptr_t)mask % 4 == 0) && (mask_pitch % 4 == 0);
         // rows per warp: whole waves of co-resident blocks (1 block per SM), each
         // segment pays 18 warm-up rows -- pick the cheaper of two wave counts
         const int sb = (w + EC_WARPS * EC_OUTW - 1) / (EC_WARPS * EC_OUTW);
@@ -780,14 +831,16 @@ int krl_good_features(kr_ctx *ctx, const uint8_t *img, int64_t pitch, const uint
         }
         const int seg = best_seg;
         dim3 grid(sb, (h + seg - 1) / seg);
-        if (aligned)
-            k_eig_stream<true><<<grid, EC_WARPS * 32, esm, s>>>(img, pitch, mask, mask_pitch, w, h, scale,
-                                                               tail_start, eig_out, eig_pitch, ctx->d_cand,
-                                                               (uint32_t)ctx->cand_cap, ctx->d_stats, emit, seg);
-        else
-            k_eig_stream<false><<<grid, EC_WARPS * 32, esm, s>>>(img, pitch, mask, mask_pitch, w, h, scale,
-                                                                tail_start, eig_out, eig_pitch, ctx->d_cand,
-                                                                (uint32_t)ctx->cand_cap, ctx->d_stats, emit, seg);
+#define KR_EIG_LAUNCH(M, D)                                                                        \
+    k_eig_stream<M, D><<<grid, EC_WARPS * 32, esm, s>>>(img, pitch, mask, mask_pitch, w, h, scale,     \
+                                                        tail_start, eig_out, eig_pitch, ctx->d_cand,   \
+                                                        (uint32_t)ctx->cand_cap, ctx->d_stats, emit,   \
+                                                        seg, aligned)
+        if (mask && eig_out) KR_EIG_LAUNCH(true, true);
+        else if (mask) KR_EIG_LAUNCH(true, false);
+        else if (eig_out) KR_EIG_LAUNCH(false, true);
+        else KR_EIG_LAUNCH(false, false);
+#undef KR_EIG_LAUNCH
     } else {
         // generic tile kernel: any blockSize <= 31, any image size
         dim3 grid((w + EG_TW - 1) / EG_TW, (h + EG_TH - 1) / EG_TH);

@@ -54,7 +54,9 @@ __global__ void __launch_bounds__(PD_WARPS * 32) k_pyr_down(PyrPair pp, int w, i
     const bool store_lane = lane >= 1 && lane <= PD_VALID && ox < dw;
 
     auto hrow = [&](int r) -> int {
-        const uint8_t *row = src + (int64_t)kr_reflect101(r, h) * sp;
+        int tr = r;
+        if ((unsigned)tr >= (unsigned)h) tr = kr_reflect101(r, h);
+        const uint8_t *row = src + (int64_t)tr * sp;
         int a0 = __ldg(row + c0), a1 = __ldg(row + c1);
         int pk = a0 | (a1 << 8);
         int lp = __shfl_up_sync(FULL, pk, 1), rp = __shfl_down_sync(FULL, pk, 1);

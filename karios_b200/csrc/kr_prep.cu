@@ -242,9 +242,21 @@ k_laplacian(const T *__restrict__ img, int64_t pitch, int w, int h, const uint8_
     for (int i = 0; i < (NS > 0 ? NS : 1); i++) vs[i] = 0;
     int e_m2 = 0, e_m1 = 0, s_m1 = 0, s_m2 = 0;
 
-    for (int r = ys - R; r < ye + R; r++) {
-        const T *row = (const T *)((const char *)img + (int64_t)kr_reflect101(r, h) * pitch);
-        int v = to_u8<T>(row[col], lut, fmn, frange, invert);
+    // software pipeline: the raw pixel is loaded two rows ahead and normalised one
+    // row ahead, so the two dependent loads (pixel, table) are off the critical path
+    auto load_raw = [&](int r) -> T {
+        int tr = r;
+        if ((unsigned)tr >= (unsigned)h) tr = kr_reflect101(r, h);
+        return *((const T *)((const char *)img + (int64_t)tr * pitch) + col);
+    };
+    const int r_first = ys - R, r_end = ye + R;
+    int v_next = to_u8<T>(load_raw(r_first), lut, fmn, frange, invert);
+    T raw_next = load_raw(r_first + 1);
+#pragma unroll 2
+    for (int r = r_first; r < r_end; r++) {
+        int v = v_next;
+        v_next = to_u8<T>(raw_next, lut, fmn, frange, invert);
+        raw_next = load_raw(r + 2);
         // horizontal binomial cascade, alternating direction to stay centred
 #pragma unroll
         for (int i = 0; i < NS; i++) {

@@ -107,8 +107,9 @@ def test_min_eigen_val(golden, N, ctx, name):
         assert np.array_equal(e, O.min_eigen_val(g["lap_ref"], block)), block
 
 
-def test_min_eigen_val_small_images(N, ctx):
+def test_min_eigen_val_small_images(N):
     rng = np.random.default_rng(9)
+    ctx = N.Context(1400, 600, 1000)
     for shape in ((1, 1), (2, 3), (5, 5), (9, 40), (33, 65), (64, 32), (16, 16), (17, 130), (300, 1301),
                   (530, 212)):
         a = rng.integers(0, 255, shape).astype(np.uint8)
