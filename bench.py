@@ -219,9 +219,11 @@ def cuda_arm(args):
     torch.cuda.synchronize()
     sm = SceneMatcher(size, size, conf, 0.4, device=dev)
 
+    from karios_b200 import sharding
+
     def step(i):
         mon, ref = scenes[i % len(scenes)]
-        return sm.match_device(mon, ref, None, collect=False)[1]
+        return sm.match_device(mon, ref, None, collect=True)
 
     for i in range(args.warmup):
         step(i)
@@ -234,16 +236,22 @@ def cuda_arm(args):
     torch.cuda.synchronize()
     e0.record()
     matches = 0
+    tables = []
     for i in range(args.steps):
-        matches += step(i)
+        tiles, n = step(i)
+        matches += n
+        tables.append(tiles)
     if world > 1:
-        # the one exchange step: gather per-rank match counts and the (padded) rows
-        # of the last scene of every rank on all ranks (NCCL all-gather, NVLink)
-        n = torch.tensor([sm.rows.capacity], device=dev, dtype=torch.int32)
-        counts = torch.empty(world, device=dev, dtype=torch.int32)
-        dist.all_gather_into_tensor(counts, n)
-        gathered = torch.empty((world,) + tuple(sm.rows.f32.shape), device=dev, dtype=torch.float32)
-        dist.all_gather_into_tensor(gathered, sm.rows.f32)
+        # the one exchange step of the path: every rank ends with the match tables of
+        # all world*steps scene pairs (all_reduce of counts + NCCL all_gather of rows)
+        # and the global dx/dy moments
+        n_units = world * args.steps
+        ids = [rank + i * world for i in range(args.steps)]
+        packed = [torch.cat([sharding.pack_rows(f, z) for f, z in t]) if t else
+                  torch.zeros((0, 6), dtype=torch.float64, device=dev) for t in tables]
+        merged = sharding.gather_matches(ids, packed, n_units)
+        sharding.gather_moments(torch.cat(packed))
+        assert len(merged) == n_units
     e1.record()
     torch.cuda.synchronize()
     sampler.stop_flag.set()

@@ -309,6 +309,68 @@ def test_sort_and_unlimited_corners(N):
     assert len(want) > 3 * 8192
 
 
+def test_full_s2_scene_properties_and_opencv():
+    """BASELINE config 2: a full 10980 x 10980 pair through SceneMatcher (one tile,
+    default config).  Size-independent properties, then -- when OpenCV is importable
+    on this box -- the same scene through the reference's OpenCV calls
+    (oracle/cv2_path.py): corners identical up to the documented ~1e-7 class of
+    one-ulp eigenvalue differences, dx/dy within 1e-3 px, ZNCC within 1e-5."""
+    from karios_b200 import synth
+    from karios_b200.api import SceneMatcher
+    from karios_b200.core.configuration import KLTConfiguration
+    size = 10980
+    ref_t, mon_t = synth.make_pair(size, size, seed=1234, device="cuda")
+    conf = KLTConfiguration()
+    sm = SceneMatcher(size, size, conf, 0.4)
+    try:
+        tiles, total = sm.match_device(mon_t, ref_t, None)
+        st = sm.ctx.read_stats()
+        df = sm.to_frame(tiles)
+    finally:
+        sm.close()
+    assert total == len(df) and 0 < total <= 20000 and st.n_corners == 20000
+    x0, y0 = df["x0"].to_numpy(), df["y0"].to_numpy()
+    key = x0.astype(np.int64) * 65536 + y0.astype(np.int64)
+    assert (np.diff(key) > 0).all()                                   # sorted by (x0, y0), unique
+    assert x0.min() >= 1 and y0.min() >= 1 and x0.max() <= size - 2 and y0.max() <= size - 2
+    # min-distance contract: no two corners closer than minDistance (grid check)
+    cell = {}
+    for x, y in zip(x0.astype(int), y0.astype(int)):
+        cell.setdefault((x // 10, y // 10), []).append((x, y))
+    for (cx, cy), pts in cell.items():
+        for ddx in (-1, 0, 1):
+            for ddy in (-1, 0, 1):
+                for (x, y) in pts:
+                    for (u, v) in cell.get((cx + ddx, cy + ddy), []):
+                        assert (u, v) == (x, y) or (x - u) ** 2 + (y - v) ** 2 >= 100
+    assert (df["score"] > 0).all() and (df["score"] <= 1).all()
+    z = df["zncc_score"].to_numpy()
+    inner = (x0 >= 30) & (y0 >= 30) & (x0 < size - 30) & (y0 < size - 30) & (df["score"].to_numpy() >= 0.4)
+    assert not np.isnan(z[inner]).any() and np.nanmax(np.abs(z)) <= 1 + 1e-9
+    assert abs(df["dx"].mean() - 0.30) < 0.1 and abs(df["dy"].mean() + 0.20) < 0.1     # the synthetic shift
+
+    from oracle import cv2_path as P
+    if not P.HAVE_CV2:
+        pytest.skip("cv2 not importable here: OpenCV comparison skipped")
+    to_np = lambda t: t.cpu().view(torch.int16).numpy().view(np.uint16)  # noqa: E731
+    ref, mon = to_np(ref_t), to_np(mon_t)
+    tiles_cv, total_cv = P.match_scene(mon, ref, None, O.KLTConfiguration())
+    c = tiles_cv[0]
+    key_cv = c["x0"].astype(np.int64) * 65536 + c["y0"].astype(np.int64)
+    common, ia, ib = np.intersect1d(key, key_cv, return_indices=True)
+    frac = len(common) / max(len(key), len(key_cv))
+    print(f"corners: gpu {len(key)} cv2 {len(key_cv)} common {len(common)} ({frac:.6f})")
+    assert frac >= 0.999
+    ddx = np.abs(df["dx"].to_numpy()[ia] - c["dx"][ib])
+    ddy = np.abs(df["dy"].to_numpy()[ia] - c["dy"][ib])
+    print(f"max |ddx| {ddx.max():.2e} max |ddy| {ddy.max():.2e} identical {(np.maximum(ddx, ddy) == 0).mean():.4f}")
+    assert ddx.max() < 1e-3 and ddy.max() < 1e-3
+    zc = c["zncc"][ib]
+    zg = z[ia]
+    assert np.array_equal(np.isnan(zc), np.isnan(zg))
+    assert np.nanmax(np.abs(zc - zg)) < 1e-5
+
+
 def test_smoke_entry():
     import __graft_entry__ as ge
     ge.smoke()
