@@ -95,49 +95,145 @@ __device__ __forceinline__ void lk_weights(float a, float b, int &w00, int &w01,
 }
 
 // Sum over the window of |J(pos) - Iw| (flag ABS) or of diff*Ix, diff*Iy, at
-// integer origin (inx, iny) with the given bilinear weights.  All lanes get
-// the totals.
-template <bool ABS>
+// integer origin (inx, iny) with the given bilinear weights.  All lanes get the
+// totals.  FAST: the (win+1)^2 footprint lies inside the image -- no border
+// arithmetic, running row pointer, next row prefetched.  WIN > 0 fixes the
+// window at compile time (unrolled rows).
+template <bool ABS, bool FAST, int WIN>
 __device__ __forceinline__ void lk_residual(const uint8_t *__restrict__ J, int64_t pJ, int w, int h,
-                                            int inx, int iny, int win, int w00, int w01, int w10,
+                                            int inx, int iny, int win_rt, int w00, int w01, int w10,
                                             int w11, const int16_t *sIw, const int32_t *sIxy,
                                             int lane, long long &o1, long long &o2)
 {
-    const int col = kr_reflect101(inx + min(lane, win), w);
+    constexpr unsigned FULL = 0xffffffffu;
+    const int win = WIN ? WIN : win_rt;
     const bool act = lane < win;
+    const int lc = act ? lane : win;
+    const int16_t *iw = sIw + (act ? lane : 0);
+    const int32_t *ixy = sIxy + (act ? lane : 0);
     int b1 = 0, b2 = 0;
-    int tv = 0, tvr = 0;
-    for (int r = 0; r <= win; r++) {
-        const uint8_t *rowp = J + (int64_t)kr_reflect101(iny + r, h) * pJ;
-        int v = __ldg(rowp + col);
-        int vr = __shfl_down_sync(0xffffffffu, v, 1);
-        if (r >= 1) {
-            int val = (tv * w00 + tvr * w01 + v * w10 + vr * w11 + (1 << (W_BITS - 5 - 1))) >> (W_BITS - 5);
-            if (act) {
-                int o = (r - 1) * win + lane;
-                int diff = val - (int)sIw[o];
+    if (FAST) {
+        const uint8_t *p = J + (int64_t)iny * pJ + (inx + lc);
+        int tv = __ldg(p);
+        int vn = __ldg(p + pJ);
+        int tvr = __shfl_down_sync(FULL, tv, 1);
+#pragma unroll 5
+        for (int r = 1; r <= win; r++) {
+            const int v = vn;
+            p += pJ;
+            if (r < win) vn = __ldg(p + pJ);
+            const int vr = __shfl_down_sync(FULL, v, 1);
+            const int val = (tv * w00 + tvr * w01 + v * w10 + vr * w11 + (1 << (W_BITS - 5 - 1))) >> (W_BITS - 5);
+            const int o = (r - 1) * win;
+            int diff = val - (int)iw[o];
+            if (!act) diff = 0;
+            if (ABS) {
+                b1 += abs(diff);
+            } else {
+                const int32_t pk = ixy[o];
+                b1 += diff * (int)(int16_t)(pk & 0xffff);
+                b2 += diff * (pk >> 16);
+            }
+            tv = v;
+            tvr = vr;
+        }
+    } else {
+        const int col = kr_reflect101(inx + lc, w);
+        int tv = 0, tvr = 0;
+        for (int r = 0; r <= win; r++) {
+            const uint8_t *rowp = J + (int64_t)kr_reflect101(iny + r, h) * pJ;
+            const int v = __ldg(rowp + col);
+            const int vr = __shfl_down_sync(FULL, v, 1);
+            if (r >= 1) {
+                const int val = (tv * w00 + tvr * w01 + v * w10 + vr * w11 + (1 << (W_BITS - 5 - 1))) >> (W_BITS - 5);
+                const int o = (r - 1) * win;
+                int diff = val - (int)iw[o];
+                if (!act) diff = 0;
                 if (ABS) {
                     b1 += abs(diff);
                 } else {
-                    int32_t pk = sIxy[o];
+                    const int32_t pk = ixy[o];
                     b1 += diff * (int)(int16_t)(pk & 0xffff);
                     b2 += diff * (pk >> 16);
                 }
             }
+            tv = v;
+            tvr = vr;
         }
-        tv = v;
-        tvr = vr;
     }
     o1 = warp_sum_ll((long long)b1);
     o2 = ABS ? 0ll : warp_sum_ll((long long)b2);
 }
 
+// Template patch of one level: Iw (5 fractional bits), Ix, Iy (Scharr, bilinear at
+// the sub-pixel origin) into shared memory, and the sums of Ix^2, IxIy, Iy^2.
+// lane <-> image column ipx - 1 + lane; rows stream through registers.
+template <bool FAST, int WIN>
+__device__ __forceinline__ void lk_patch(const uint8_t *__restrict__ I, int64_t pI, int w, int h, int ipx,
+                                         int ipy, int win_rt, int w00, int w01, int w10, int w11,
+                                         int16_t *sIw, int32_t *sIxy, int lane, long long &S11,
+                                         long long &S12, long long &S22)
+{
+    constexpr unsigned FULL = 0xffffffffu;
+    const int win = WIN ? WIN : win_rt;
+    const int cx = ipx - 1 + min(lane, win + 2);
+    const int col = FAST ? cx : kr_reflect101(cx, w);
+    const bool col_in = FAST || (cx >= 0 && cx < w);
+    const bool act = lane >= 1 && lane <= win;
+    int16_t *iw = sIw + (act ? lane - 1 : 0);
+    int32_t *ixy = sIxy + (act ? lane - 1 : 0);
+    int a = 0, b = 0, c = 0;
+    int t_dx = 0, t_dxr = 0, t_dy = 0, t_dyr = 0, t_pv = 0, t_pvr = 0;
+    int s11 = 0, s12 = 0, s22 = 0;
+    const uint8_t *p = I + (FAST ? ((int64_t)(ipy - 1) * pI + col) : (int64_t)col);
+    int cn = FAST ? (int)__ldg(p) : 0;                     // prefetched next row (FAST)
+    __syncwarp();
+#pragma unroll 4
+    for (int r = 0; r < win + 3; r++) {
+        const int ry = ipy - 1 + r;
+        a = b; b = c;
+        if (FAST) {
+            c = cn;
+            p += pI;
+            if (r < win + 2) cn = __ldg(p);
+        } else {
+            c = __ldg(p + (int64_t)kr_reflect101(ry, h) * pI);
+        }
+        if (r < 2) continue;
+        const int Y = ry - 1;                   // row of the derivative being formed
+        const int S = 3 * (a + c) + 10 * b, D = c - a;
+        const int Sl = __shfl_up_sync(FULL, S, 1), Sr = __shfl_down_sync(FULL, S, 1);
+        const int Dl = __shfl_up_sync(FULL, D, 1), Dr = __shfl_down_sync(FULL, D, 1);
+        int dxv = Sr - Sl, dyv = 3 * (Dl + Dr) + 10 * D;
+        if (!FAST && !(col_in && Y >= 0 && Y < h)) { dxv = 0; dyv = 0; }    // derivative border = 0
+        const int pv = b;
+        const int dxr = __shfl_down_sync(FULL, dxv, 1);
+        const int dyr = __shfl_down_sync(FULL, dyv, 1);
+        const int pvr = __shfl_down_sync(FULL, pv, 1);
+        if (r >= 3 && act) {
+            const int ix = (t_dx * w00 + t_dxr * w01 + dxv * w10 + dxr * w11 + (1 << (W_BITS - 1))) >> W_BITS;
+            const int iy = (t_dy * w00 + t_dyr * w01 + dyv * w10 + dyr * w11 + (1 << (W_BITS - 1))) >> W_BITS;
+            const int iv = (t_pv * w00 + t_pvr * w01 + pv * w10 + pvr * w11 + (1 << (W_BITS - 5 - 1))) >> (W_BITS - 5);
+            const int o = (r - 3) * win;
+            iw[o] = (int16_t)iv;
+            ixy[o] = (int32_t)((uint32_t)(ix & 0xffff) | ((uint32_t)iy << 16));
+            s11 += ix * ix; s12 += ix * iy; s22 += iy * iy;
+        }
+        t_dx = dxv; t_dxr = dxr; t_dy = dyv; t_dyr = dyr; t_pv = pv; t_pvr = pvr;
+    }
+    __syncwarp();
+    S11 = warp_sum_ll((long long)s11);
+    S12 = warp_sum_ll((long long)s12);
+    S22 = warp_sum_ll((long long)s22);
+}
+
 // calcOpticalFlowPyrLK for one point, all levels, direction dir (0: img[0] is
 // the previous image, 1: img[1] is).  Uniform across the warp.
+template <int WIN>
 __device__ void lk_track(const KrLkArgs &A, int dir, float ptx, float pty, float &ox, float &oy,
                          uint8_t &status, float &err, int16_t *sIw, int32_t *sIxy, int lane)
 {
-    const int win = A.win;
+    const int win = WIN ? WIN : A.win;
     const float half = __fmul_rn((float)(win - 1), 0.5f);
     const float FLT_SCALE = 1.f / (float)(1 << 20);
     status = 1;
@@ -164,96 +260,66 @@ __device__ void lk_track(const KrLkArgs &A, int dir, float ptx, float pty, float
         int w00, w01, w10, w11;
         lk_weights(__fsub_rn(px, (float)ipx), __fsub_rn(py, (float)ipy), w00, w01, w10, w11);
 
-        // ---- template patch: lane <-> image column ipx - 1 + lane ----------
-        {
-            const int cx = ipx - 1 + min(lane, win + 2);
-            const int col = kr_reflect101(cx, w);
-            const bool col_in = cx >= 0 && cx < w;
-            const bool act = lane >= 1 && lane <= win;
-            int a = 0, b = 0, c = 0;
-            int t_dx = 0, t_dxr = 0, t_dy = 0, t_dyr = 0, t_pv = 0, t_pvr = 0;
-            int s11 = 0, s12 = 0, s22 = 0;
-            __syncwarp();
-            for (int r = 0; r < win + 3; r++) {
-                const int ry = ipy - 1 + r;
-                a = b; b = c;
-                c = __ldg(I + (int64_t)kr_reflect101(ry, h) * pI + col);
-                if (r < 2) continue;
-                const int Y = ry - 1;                   // row of the derivative being formed
-                int S = 3 * (a + c) + 10 * b, D = c - a;
-                int Sl = __shfl_up_sync(0xffffffffu, S, 1), Sr = __shfl_down_sync(0xffffffffu, S, 1);
-                int Dl = __shfl_up_sync(0xffffffffu, D, 1), Dr = __shfl_down_sync(0xffffffffu, D, 1);
-                int dxv = Sr - Sl, dyv = 3 * (Dl + Dr) + 10 * D;
-                if (!(col_in && Y >= 0 && Y < h)) { dxv = 0; dyv = 0; }    // derivative border = 0
-                int pv = b;
-                int dxr = __shfl_down_sync(0xffffffffu, dxv, 1);
-                int dyr = __shfl_down_sync(0xffffffffu, dyv, 1);
-                int pvr = __shfl_down_sync(0xffffffffu, pv, 1);
-                if (r >= 3 && act) {
-                    int y = r - 3;
-                    int ix = (t_dx * w00 + t_dxr * w01 + dxv * w10 + dxr * w11 + (1 << (W_BITS - 1))) >> W_BITS;
-                    int iy = (t_dy * w00 + t_dyr * w01 + dyv * w10 + dyr * w11 + (1 << (W_BITS - 1))) >> W_BITS;
-                    int iv = (t_pv * w00 + t_pvr * w01 + pv * w10 + pvr * w11 + (1 << (W_BITS - 5 - 1))) >> (W_BITS - 5);
-                    int o = y * win + (lane - 1);
-                    sIw[o] = (int16_t)iv;
-                    sIxy[o] = (int32_t)((uint32_t)(ix & 0xffff) | ((uint32_t)iy << 16));
-                    s11 += ix * ix; s12 += ix * iy; s22 += iy * iy;
-                }
-                t_dx = dxv; t_dxr = dxr; t_dy = dyv; t_dyr = dyr; t_pv = pv; t_pvr = pvr;
-            }
-            __syncwarp();
-            const long long S11 = warp_sum_ll((long long)s11), S12 = warp_sum_ll((long long)s12),
-                            S22 = warp_sum_ll((long long)s22);
-            const float A11 = __fmul_rn((float)S11, FLT_SCALE), A12 = __fmul_rn((float)S12, FLT_SCALE),
-                        A22 = __fmul_rn((float)S22, FLT_SCALE);
-            float Dt = __fsub_rn(__fmul_rn(A11, A22), __fmul_rn(A12, A12));
-            const float dd = __fsub_rn(A11, A22);
-            const float rad = __fadd_rn(__fmul_rn(dd, dd), __fmul_rn(__fmul_rn(4.f, A12), A12));
-            const float min_eig = __fdiv_rn(__fsub_rn(__fadd_rn(A22, A11), __fsqrt_rn(rad)),
-                                            (float)(2 * win * win));
-            if (min_eig < A.min_eig_thr || Dt < FLT_EPSILON) {
-                if (l == 0) status = 0;
-                continue;
-            }
-            Dt = __fdiv_rn(1.f, Dt);
+        long long S11, S12, S22;
+        if (ipx >= 1 && ipy >= 1 && ipx + win + 1 < w && ipy + win + 1 < h)
+            lk_patch<true, WIN>(I, pI, w, h, ipx, ipy, win, w00, w01, w10, w11, sIw, sIxy, lane, S11, S12, S22);
+        else
+            lk_patch<false, WIN>(I, pI, w, h, ipx, ipy, win, w00, w01, w10, w11, sIw, sIxy, lane, S11, S12, S22);
+        const float A11 = __fmul_rn((float)S11, FLT_SCALE), A12 = __fmul_rn((float)S12, FLT_SCALE),
+                    A22 = __fmul_rn((float)S22, FLT_SCALE);
+        float Dt = __fsub_rn(__fmul_rn(A11, A22), __fmul_rn(A12, A12));
+        const float dd = __fsub_rn(A11, A22);
+        const float rad = __fadd_rn(__fmul_rn(dd, dd), __fmul_rn(__fmul_rn(4.f, A12), A12));
+        const float min_eig = __fdiv_rn(__fsub_rn(__fadd_rn(A22, A11), __fsqrt_rn(rad)),
+                                        (float)(2 * win * win));
+        if (min_eig < A.min_eig_thr || Dt < FLT_EPSILON) {
+            if (l == 0) status = 0;
+            continue;
+        }
+        Dt = __fdiv_rn(1.f, Dt);
 
-            // ---- iterations on J ------------------------------------------
-            nx = __fsub_rn(nx, half); ny = __fsub_rn(ny, half);
-            float pdx = 0.f, pdy = 0.f;
-            for (int j = 0; j < A.max_count; j++) {
-                const int inx = (int)floorf(nx), iny = (int)floorf(ny);
-                if (inx < -win || inx >= w || iny < -win || iny >= h) {
-                    if (l == 0) status = 0;
-                    break;
-                }
-                lk_weights(__fsub_rn(nx, (float)inx), __fsub_rn(ny, (float)iny), w00, w01, w10, w11);
-                long long sb1, sb2;
-                lk_residual<false>(J, pJ, w, h, inx, iny, win, w00, w01, w10, w11, sIw, sIxy, lane, sb1, sb2);
-                const float b1 = __fmul_rn((float)sb1, FLT_SCALE), b2 = __fmul_rn((float)sb2, FLT_SCALE);
-                const float ddx = __fmul_rn(__fsub_rn(__fmul_rn(A12, b2), __fmul_rn(A22, b1)), Dt);
-                const float ddy = __fmul_rn(__fsub_rn(__fmul_rn(A12, b1), __fmul_rn(A11, b2)), Dt);
-                nx = __fadd_rn(nx, ddx); ny = __fadd_rn(ny, ddy);
-                ox = __fadd_rn(nx, half); oy = __fadd_rn(ny, half);
-                if ((double)ddx * (double)ddx + (double)ddy * (double)ddy <= A.eps2) break;
-                if (j > 0 && fabs((double)__fadd_rn(ddx, pdx)) < 0.01 &&
-                    fabs((double)__fadd_rn(ddy, pdy)) < 0.01) {
-                    ox = __fsub_rn(ox, __fmul_rn(ddx, 0.5f));
-                    oy = __fsub_rn(oy, __fmul_rn(ddy, 0.5f));
-                    break;
-                }
-                pdx = ddx; pdy = ddy;
+        // ---- iterations on J ----------------------------------------------
+        nx = __fsub_rn(nx, half); ny = __fsub_rn(ny, half);
+        float pdx = 0.f, pdy = 0.f;
+        for (int j = 0; j < A.max_count; j++) {
+            const int inx = (int)floorf(nx), iny = (int)floorf(ny);
+            if (inx < -win || inx >= w || iny < -win || iny >= h) {
+                if (l == 0) status = 0;
+                break;
             }
-            if (status && l == 0) {
-                const float ex = __fsub_rn(ox, half), ey = __fsub_rn(oy, half);
-                const int iex = (int)floorf(ex), iey = (int)floorf(ey);
-                if (iex < -win || iex >= w || iey < -win || iey >= h) {
-                    status = 0;
-                } else {
-                    lk_weights(__fsub_rn(ex, (float)iex), __fsub_rn(ey, (float)iey), w00, w01, w10, w11);
-                    long long sabs, dummy;
-                    lk_residual<true>(J, pJ, w, h, iex, iey, win, w00, w01, w10, w11, sIw, sIxy, lane, sabs, dummy);
-                    err = __fdiv_rn(__fmul_rn((float)sabs, 1.f), (float)(32 * win * win));
-                }
+            lk_weights(__fsub_rn(nx, (float)inx), __fsub_rn(ny, (float)iny), w00, w01, w10, w11);
+            long long sb1, sb2;
+            if (inx >= 0 && iny >= 0 && inx + win < w && iny + win < h)
+                lk_residual<false, true, WIN>(J, pJ, w, h, inx, iny, win, w00, w01, w10, w11, sIw, sIxy, lane, sb1, sb2);
+            else
+                lk_residual<false, false, WIN>(J, pJ, w, h, inx, iny, win, w00, w01, w10, w11, sIw, sIxy, lane, sb1, sb2);
+            const float b1 = __fmul_rn((float)sb1, FLT_SCALE), b2 = __fmul_rn((float)sb2, FLT_SCALE);
+            const float ddx = __fmul_rn(__fsub_rn(__fmul_rn(A12, b2), __fmul_rn(A22, b1)), Dt);
+            const float ddy = __fmul_rn(__fsub_rn(__fmul_rn(A12, b1), __fmul_rn(A11, b2)), Dt);
+            nx = __fadd_rn(nx, ddx); ny = __fadd_rn(ny, ddy);
+            ox = __fadd_rn(nx, half); oy = __fadd_rn(ny, half);
+            if ((double)ddx * (double)ddx + (double)ddy * (double)ddy <= A.eps2) break;
+            if (j > 0 && fabs((double)__fadd_rn(ddx, pdx)) < 0.01 &&
+                fabs((double)__fadd_rn(ddy, pdy)) < 0.01) {
+                ox = __fsub_rn(ox, __fmul_rn(ddx, 0.5f));
+                oy = __fsub_rn(oy, __fmul_rn(ddy, 0.5f));
+                break;
+            }
+            pdx = ddx; pdy = ddy;
+        }
+        if (status && l == 0) {
+            const float ex = __fsub_rn(ox, half), ey = __fsub_rn(oy, half);
+            const int iex = (int)floorf(ex), iey = (int)floorf(ey);
+            if (iex < -win || iex >= w || iey < -win || iey >= h) {
+                status = 0;
+            } else {
+                lk_weights(__fsub_rn(ex, (float)iex), __fsub_rn(ey, (float)iey), w00, w01, w10, w11);
+                long long sabs, dummy;
+                if (iex >= 0 && iey >= 0 && iex + win < w && iey + win < h)
+                    lk_residual<true, true, WIN>(J, pJ, w, h, iex, iey, win, w00, w01, w10, w11, sIw, sIxy, lane, sabs, dummy);
+                else
+                    lk_residual<true, false, WIN>(J, pJ, w, h, iex, iey, win, w00, w01, w10, w11, sIw, sIxy, lane, sabs, dummy);
+                err = __fdiv_rn(__fmul_rn((float)sabs, 1.f), (float)(32 * win * win));
             }
         }
     }
@@ -265,6 +331,7 @@ __device__ __forceinline__ int lk_count(int n, const int32_t *d_count)
     return n;
 }
 
+template <int WIN>
 __global__ void __launch_bounds__(LK_WARPS * 32)
 k_lk_single(KrLkArgs A, const float *__restrict__ p0, int n, const int32_t *d_count,
             float *__restrict__ p1, uint8_t *__restrict__ status, float *__restrict__ err)
@@ -278,7 +345,7 @@ k_lk_single(KrLkArgs A, const float *__restrict__ p0, int n, const int32_t *d_co
     for (int i = blockIdx.x * LK_WARPS + wid; i < cnt; i += gridDim.x * LK_WARPS) {
         float ox, oy, e;
         uint8_t st;
-        lk_track(A, 0, p0[2 * i], p0[2 * i + 1], ox, oy, st, e, sIw, sIxy, lane);
+        lk_track<WIN>(A, 0, p0[2 * i], p0[2 * i + 1], ox, oy, st, e, sIw, sIxy, lane);
         if (lane == 0) {
             p1[2 * i] = ox; p1[2 * i + 1] = oy;
             status[i] = st;
@@ -289,6 +356,7 @@ k_lk_single(KrLkArgs A, const float *__restrict__ p0, int n, const int32_t *d_co
 
 // forward (ref -> mon), backward (mon -> ref) from the forward result, then the
 // back-check of klt.py:142-144: d = max|p0 - p0r|, keep = d < 0.1 (float32).
+template <int WIN>
 __global__ void __launch_bounds__(LK_WARPS * 32)
 k_lk_roundtrip(KrLkArgs A, const float *__restrict__ p0, int n_cap, const uint32_t *d_count,
                float back_thr, float *__restrict__ p1, float *__restrict__ dist,
@@ -304,8 +372,8 @@ k_lk_roundtrip(KrLkArgs A, const float *__restrict__ p0, int n_cap, const uint32
         const float x0 = p0[2 * i], y0 = p0[2 * i + 1];
         float x1, y1, xr, yr, e;
         uint8_t st;
-        lk_track(A, 0, x0, y0, x1, y1, st, e, sIw, sIxy, lane);
-        lk_track(A, 1, x1, y1, xr, yr, st, e, sIw, sIxy, lane);
+        lk_track<WIN>(A, 0, x0, y0, x1, y1, st, e, sIw, sIxy, lane);
+        lk_track<WIN>(A, 1, x1, y1, xr, yr, st, e, sIw, sIxy, lane);
         if (lane == 0) {
             float d = fmaxf(fabsf(__fsub_rn(x0, xr)), fabsf(__fsub_rn(y0, yr)));
             p1[2 * i] = x1; p1[2 * i + 1] = y1;
@@ -375,8 +443,8 @@ int lk_prepare(const KrLkArgs &a, size_t *smem)
     *smem = lk_smem_bytes(a.win);
     static size_t set1 = 0;
     if (*smem > set1 && *smem > 48 * 1024) {
-        KR_CUDA(cudaFuncSetAttribute(k_lk_single, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)*smem));
-        KR_CUDA(cudaFuncSetAttribute(k_lk_roundtrip, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)*smem));
+        KR_CUDA(cudaFuncSetAttribute(k_lk_single<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)*smem));
+        KR_CUDA(cudaFuncSetAttribute(k_lk_roundtrip<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)*smem));
         set1 = *smem;
     }
     return KR_OK;
@@ -440,7 +508,8 @@ int krl_lk_single(const KrLkArgs &a, const float *p0, int n, const int32_t *d_co
     KR_TRY(lk_prepare(a, &smem));
     if (n <= 0) return KR_OK;
     int grid = (n + LK_WARPS - 1) / LK_WARPS;
-    k_lk_single<<<grid, LK_WARPS * 32, smem, s>>>(a, p0, n, d_count, p1, status, err);
+    if (a.win == 25) k_lk_single<25><<<grid, LK_WARPS * 32, smem, s>>>(a, p0, n, d_count, p1, status, err);
+    else k_lk_single<0><<<grid, LK_WARPS * 32, smem, s>>>(a, p0, n, d_count, p1, status, err);
     KR_LAUNCH_CHECK();
     return KR_OK;
 }
@@ -453,7 +522,10 @@ int krl_lk_roundtrip(const KrLkArgs &a, const float *p0, int n_cap, const uint32
     if (n_cap <= 0) return KR_OK;
     int grid = (n_cap + LK_WARPS - 1) / LK_WARPS;
     if (grid > 65535 * 8) grid = 65535 * 8;
-    k_lk_roundtrip<<<grid, LK_WARPS * 32, smem, s>>>(a, p0, n_cap, d_count, back_thr, p1, dist, keep);
+    if (a.win == 25)
+        k_lk_roundtrip<25><<<grid, LK_WARPS * 32, smem, s>>>(a, p0, n_cap, d_count, back_thr, p1, dist, keep);
+    else
+        k_lk_roundtrip<0><<<grid, LK_WARPS * 32, smem, s>>>(a, p0, n_cap, d_count, back_thr, p1, dist, keep);
     KR_LAUNCH_CHECK();
     return KR_OK;
 }
