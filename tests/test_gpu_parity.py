@@ -369,6 +369,15 @@ def test_full_s2_scene_properties_and_opencv():
     zg = z[ia]
     assert np.array_equal(np.isnan(zc), np.isnan(zg))
     assert np.nanmax(np.abs(zc - zg)) < 1e-5
+    import json
+    import os
+    out = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+    if os.path.isdir(out):
+        json.dump({"corners_gpu": int(len(key)), "corners_cv2": int(len(key_cv)), "common": int(len(common)),
+                   "max_abs_ddx": float(ddx.max()), "max_abs_ddy": float(ddy.max()),
+                   "bit_identical_fraction": float((np.maximum(ddx, ddy) == 0).mean()),
+                   "zncc_max_abs_diff": float(np.nanmax(np.abs(zc - zg)))},
+                  open(os.path.join(out, "full_scene_parity.json"), "w"))
 
 
 def test_smoke_entry():
