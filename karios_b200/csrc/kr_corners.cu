@@ -259,7 +259,8 @@ k_eig_candidates(const uint8_t *__restrict__ img, int64_t pitch, const uint8_t *
 // the two neighbours swapped, which reproduces the product AT the reflected
 // position.  float64 sums of these float32 products are exact in all but
 // ~1e-7 of the pixels, so the summation order is free.
-constexpr int EC_WARPS = 8, EC_OUTW = 104, EC_LEFT = 12, EC_CBUF = 256;
+constexpr int EC_WARPS = 4, EC_BLOCKS_PER_SM = 3, EC_OUTW = 104, EC_LEFT = 12, EC_CBUF = 256;
+constexpr int EC_RING_F4 = 16 * 2 * 32;          // float4 per warp: 16 rows x (dx, dy) x 32 lanes
 
 __device__ __forceinline__ float eig_from_sums(double sxx, double sxy, double syy)
 {
@@ -364,33 +365,35 @@ __device__ __forceinline__ void eig_stream_body(
         if (r >= r_first + 2) {
             // ---- products of (virtual) row r-1 ------------------------------
             const bool rrefl = (r - 1) < 0 || (r - 1) >= h;
-            float px[3][4];
+            float dxv[4], dyv[4];
 #pragma unroll
             for (int j = 0; j < 4; j++) {
-                const float dx = __fmaf_rn(s, (float)(R2[j] + R0[j]), __fmul_rn(s2, (float)R1[j]));
+                dxv[j] = __fmaf_rn(s, (float)(R2[j] + R0[j]), __fmul_rn(s2, (float)R1[j]));
                 const float d0 = __fsub_rn(T0[j], T2[j]);
-                const float dy = rrefl ? -d0 : d0;           // exact negation
-                px[0][j] = __fmul_rn(dx, dx);
-                px[1][j] = __fmul_rn(dx, dy);
-                px[2][j] = __fmul_rn(dy, dy);
+                dyv[j] = rrefl ? -d0 : d0;                   // exact negation
             }
-            // ---- vertical running sums (float64), ring of float32 products ---
+            // ---- vertical running sums (float64); the ring keeps (dx, dy) of the
+            //      last 15 product rows as float32, products are re-formed on exit
             nprod++;
             const int rd_slot = r & 15, wr_slot = (r - 1) & 15;
             if (nprod > 15) {
+                const float4 ox = ring[(rd_slot * 2 + 0) * 32], oy = ring[(rd_slot * 2 + 1) * 32];
+                const float odx[4] = {ox.x, ox.y, ox.z, ox.w}, ody[4] = {oy.x, oy.y, oy.z, oy.w};
 #pragma unroll
-                for (int c = 0; c < 3; c++) {
-                    const float4 o = ring[(rd_slot * 3 + c) * 32];
-                    cs[c][0] -= (double)o.x; cs[c][1] -= (double)o.y;
-                    cs[c][2] -= (double)o.z; cs[c][3] -= (double)o.w;
+                for (int j = 0; j < 4; j++) {
+                    cs[0][j] -= (double)__fmul_rn(odx[j], odx[j]);
+                    cs[1][j] -= (double)__fmul_rn(odx[j], ody[j]);
+                    cs[2][j] -= (double)__fmul_rn(ody[j], ody[j]);
                 }
             }
 #pragma unroll
-            for (int c = 0; c < 3; c++) {
-                cs[c][0] += (double)px[c][0]; cs[c][1] += (double)px[c][1];
-                cs[c][2] += (double)px[c][2]; cs[c][3] += (double)px[c][3];
-                ring[(wr_slot * 3 + c) * 32] = make_float4(px[c][0], px[c][1], px[c][2], px[c][3]);
+            for (int j = 0; j < 4; j++) {
+                cs[0][j] += (double)__fmul_rn(dxv[j], dxv[j]);
+                cs[1][j] += (double)__fmul_rn(dxv[j], dyv[j]);
+                cs[2][j] += (double)__fmul_rn(dyv[j], dyv[j]);
             }
+            ring[(wr_slot * 2 + 0) * 32] = make_float4(dxv[0], dxv[1], dxv[2], dxv[3]);
+            ring[(wr_slot * 2 + 1) * 32] = make_float4(dyv[0], dyv[1], dyv[2], dyv[3]);
             if (nprod >= 15) {
                 // ---- horizontal 15-column sums -> eigenvalue row r - 8 --------
                 float E0[6];
@@ -481,7 +484,7 @@ __device__ __forceinline__ void eig_stream_body(
 }
 
 template <bool HAS_MASK, bool DEBUG_EIG>
-__global__ void __launch_bounds__(EC_WARPS * 32, 1)
+__global__ void __launch_bounds__(EC_WARPS * 32, EC_BLOCKS_PER_SM)
 k_eig_stream(const uint8_t *__restrict__ img, int64_t pitch, const uint8_t *__restrict__ mask,
              int64_t mpitch, int w, int h, float s, int tail_start, float *__restrict__ eig_out,
              int64_t eig_pitch, uint64_t *__restrict__ cand, uint32_t cand_cap, KrDevStats *st, int emit,
@@ -489,8 +492,8 @@ k_eig_stream(const uint8_t *__restrict__ img, int64_t pitch, const uint8_t *__re
 {
     extern __shared__ __align__(16) unsigned char ec_smem[];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    float4 *ring = reinterpret_cast<float4 *>(ec_smem) + (size_t)wid * 16 * 3 * 32 + lane;   // [16][3][32]
-    uint64_t *cbuf = reinterpret_cast<uint64_t *>(ec_smem + (size_t)EC_WARPS * 16 * 3 * 32 * 16) +
+    float4 *ring = reinterpret_cast<float4 *>(ec_smem) + (size_t)wid * EC_RING_F4 + lane;     // [16][2][32]
+    uint64_t *cbuf = reinterpret_cast<uint64_t *>(ec_smem + (size_t)EC_WARPS * EC_RING_F4 * 16) +
                      (size_t)wid * EC_CBUF;
     const int xs = (blockIdx.x * EC_WARPS + wid) * EC_OUTW;        // first output column
     if (xs >= w) return;
@@ -803,7 +806,7 @@ int krl_good_features(kr_ctx *ctx, const uint8_t *img, int64_t pitch, const uint
     k_clear_counts<<<1, 1, 0, s>>>(ctx->d_stats);
     KR_LAUNCH_CHECK();
     if (block == 15 && w >= 16 && h >= 16) {
-        const size_t esm = (size_t)EC_WARPS * (16 * 3 * 32 * 16 + EC_CBUF * 8);
+        const size_t esm = (size_t)EC_WARPS * (EC_RING_F4 * 16 + EC_CBUF * 8);
         static bool ec_set = false;
         if (!ec_set) {
             KR_CUDA(cudaFuncSetAttribute(k_eig_stream<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)esm));
@@ -814,18 +817,19 @@ int krl_good_features(kr_ctx *ctx, const uint8_t *img, int64_t pitch, const uint
         }
         int aligned = ((uintptr_t)img % 4 == 0) && (pitch % 4 == 0);
         if (mask) aligned = aligned && ((uintptr_t)mask % 4 == 0) && (mask_pitch % 4 == 0);
-        // rows per warp: whole waves of co-resident blocks (1 block per SM), each
+        // rows per warp: whole waves of co-resident blocks (EC_BLOCKS_PER_SM per SM), each
         // segment pays 18 warm-up rows -- pick the cheaper of two wave counts
         const int sb = (w + EC_WARPS * EC_OUTW - 1) / (EC_WARPS * EC_OUTW);
         int best_seg = h, best_cost = INT_MAX;
-        const int w0 = (int)(((int64_t)sb * ((h + 255) / 256) + ctx->num_sms - 1) / ctx->num_sms);
+        const int slots = ctx->num_sms * EC_BLOCKS_PER_SM;
+        const int w0 = (int)(((int64_t)sb * ((h + 255) / 256) + slots - 1) / slots);
         for (int waves = (w0 > 1 ? w0 - 1 : 1); waves <= w0 + 1; waves++) {
-            int segs = waves * ctx->num_sms / sb;
+            int segs = waves * slots / sb;
             if (segs < 1) segs = 1;
             int sg = (h + segs - 1) / segs;
             if (sg < 32) sg = 32;
             int nseg = (h + sg - 1) / sg;
-            int wv = (sb * nseg + ctx->num_sms - 1) / ctx->num_sms;
+            int wv = (sb * nseg + slots - 1) / slots;
             int cost = wv * (sg + 18);
             if (cost < best_cost) { best_cost = cost; best_seg = sg; }
         }

@@ -24,7 +24,7 @@
 namespace {
 
 // ---------------------------------------------------------------- K5 pyrDown
-constexpr int PD_WARPS = 8, PD_ROWS = 32, PD_VALID = 30;
+constexpr int PD_WARPS = 8, PD_ROWS = 32, PD_VALID = 60;
 
 struct PyrPair {
     const uint8_t *src[2];
@@ -33,43 +33,69 @@ struct PyrPair {
 };
 
 // cv::pyrDown: [1,4,6,4,1] x [1,4,6,4,1], REFLECT_101, (sum + 128) >> 8, output
-// ((w+1)/2, (h+1)/2).  One warp walks down a strip of 30 output columns: lane <->
-// output column, each input row is two byte loads per lane (columns 2x, 2x+1),
-// the horizontal taps of the neighbours come from two warp shuffles of the
-// packed pair, the five vertical taps slide through registers (two new input
+// ((w+1)/2, (h+1)/2).  One warp walks down a strip of 60 output columns: lane <->
+// two output columns = four input columns (one aligned 32-bit load per lane and
+// input row), the taps that belong to the neighbour lanes arrive by two warp
+// shuffles of the packed word, the horizontal 5-tap sums are two dp4a, the five
+// vertical taps slide through registers as packed 16-bit pairs (two new input
 // rows per output row).  No shared memory.
-__global__ void __launch_bounds__(PD_WARPS * 32) k_pyr_down(PyrPair pp, int w, int h)
+__device__ __forceinline__ uint32_t pd_hrow(const uint8_t *__restrict__ src, int64_t sp, int w, int h, int r,
+                                            int cx, bool vec, const int *tc)
 {
     constexpr unsigned FULL = 0xffffffffu;
+    int tr = r;
+    if ((unsigned)tr >= (unsigned)h) tr = kr_reflect101(r, h);
+    const uint8_t *row = src + (int64_t)tr * sp;
+    uint32_t cur;
+    if (vec) cur = __ldg(reinterpret_cast<const uint32_t *>(row + cx));
+    else
+        cur = (uint32_t)__ldg(row + tc[0]) | ((uint32_t)__ldg(row + tc[1]) << 8) |
+              ((uint32_t)__ldg(row + tc[2]) << 16) | ((uint32_t)__ldg(row + tc[3]) << 24);
+    const uint32_t lw = __shfl_up_sync(FULL, cur, 1), rw = __shfl_down_sync(FULL, cur, 1);
+    // output 0 (input centre a0): L.a2 + 4 L.a3 + 6 a0 + 4 a1 + a2
+    const uint32_t w0 = __byte_perm(lw, cur, 0x5432);            // bytes (L.a2, L.a3, a0, a1)
+    const uint32_t h0 = __dp4a(w0, 0x04060401u, (cur >> 16) & 255u);
+    // output 1 (input centre a2): a0 + 4 a1 + 6 a2 + 4 a3 + R.a0
+    const uint32_t h1 = __dp4a(cur, 0x04060401u, rw & 255u);
+    return h0 | (h1 << 16);                                     // each <= 4080
+}
+
+__global__ void __launch_bounds__(PD_WARPS * 32) k_pyr_down(PyrPair pp, int w, int h, int aligned)
+{
     const uint8_t *__restrict__ src = pp.src[blockIdx.z];
     uint8_t *__restrict__ dst = pp.dst[blockIdx.z];
     const int64_t sp = pp.src_pitch[blockIdx.z], dp = pp.dst_pitch[blockIdx.z];
     const int dw = (w + 1) >> 1, dh = (h + 1) >> 1;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const int xs = (blockIdx.x * PD_WARPS + wid) * PD_VALID;
+    const int xs = (blockIdx.x * PD_WARPS + wid) * PD_VALID;      // first output column of the warp
     if (xs >= dw) return;
     const int oys = blockIdx.y * PD_ROWS, oye = min(oys + PD_ROWS, dh);
-    const int ox = xs + lane - 1;
-    const int c0 = kr_reflect101(2 * ox, w), c1 = kr_reflect101(2 * ox + 1, w);
-    const bool store_lane = lane >= 1 && lane <= PD_VALID && ox < dw;
+    const int ox = xs + 2 * (lane - 1);                            // two outputs: ox, ox + 1
+    const int cx = 2 * ox;                                         // four inputs: cx .. cx + 3
+    int tc[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++) tc[j] = kr_reflect101(cx + j, w);
+    const bool vec = aligned && (2 * xs - 4 >= 0) && (2 * xs - 4 + 128 <= w);
+    const bool lane_ok = lane >= 1 && lane <= 30;
+    const bool st0 = lane_ok && ox < dw, st1 = lane_ok && ox + 1 < dw;
 
-    auto hrow = [&](int r) -> int {
-        int tr = r;
-        if ((unsigned)tr >= (unsigned)h) tr = kr_reflect101(r, h);
-        const uint8_t *row = src + (int64_t)tr * sp;
-        int a0 = __ldg(row + c0), a1 = __ldg(row + c1);
-        int pk = a0 | (a1 << 8);
-        int lp = __shfl_up_sync(FULL, pk, 1), rp = __shfl_down_sync(FULL, pk, 1);
-        // p(2x-2) + 4 p(2x-1) + 6 p(2x) + 4 p(2x+1) + p(2x+2)
-        return (lp & 255) + 4 * (lp >> 8) + 6 * a0 + 4 * a1 + (rp & 255);
-    };
-
-    int r = 2 * oys - 2;
-    int h0 = hrow(r), h1 = hrow(r + 1), h2 = hrow(r + 2);
+    const int r = 2 * oys - 2;
+    uint32_t h0 = pd_hrow(src, sp, w, h, r, cx, vec, tc), h1 = pd_hrow(src, sp, w, h, r + 1, cx, vec, tc),
+             h2 = pd_hrow(src, sp, w, h, r + 2, cx, vec, tc);
+#pragma unroll 2
     for (int oy = oys; oy < oye; oy++) {
-        int h3 = hrow(2 * oy + 1), h4 = hrow(2 * oy + 2);
-        int acc = h0 + h4 + 4 * (h1 + h3) + 6 * h2;
-        if (store_lane) dst[(int64_t)oy * dp + ox] = (uint8_t)((acc + 128) >> 8);
+        const uint32_t h3 = pd_hrow(src, sp, w, h, 2 * oy + 1, cx, vec, tc),
+                       h4 = pd_hrow(src, sp, w, h, 2 * oy + 2, cx, vec, tc);
+        // packed 16-bit pairs: (h0 + h4) + 4 (h1 + h3) + 6 h2 <= 16 * 4080 = 65280 per field
+        const uint32_t acc = h0 + h4 + 4u * (h1 + h3) + 6u * h2 + 0x00800080u;
+        const uint32_t o0 = (acc >> 8) & 255u, o1 = acc >> 24;
+        uint8_t *orow = dst + (int64_t)oy * dp + ox;
+        if (vec) {
+            if (lane_ok) *reinterpret_cast<uint16_t *>(orow) = (uint16_t)(o0 | (o1 << 8));
+        } else {
+            if (st0) orow[0] = (uint8_t)o0;
+            if (st1) orow[1] = (uint8_t)o1;
+        }
         h0 = h2; h1 = h3; h2 = h4;
     }
 }
@@ -460,7 +486,9 @@ int krl_pyr_down(const uint8_t *src, int64_t pitch, int w, int h, uint8_t *dst, 
     pp.src_pitch[0] = pp.src_pitch[1] = pitch; pp.dst_pitch[0] = pp.dst_pitch[1] = dst_pitch;
     int dw = (w + 1) / 2, dh = (h + 1) / 2;
     dim3 grid((dw + PD_WARPS * PD_VALID - 1) / (PD_WARPS * PD_VALID), (dh + PD_ROWS - 1) / PD_ROWS, 1);
-    k_pyr_down<<<grid, PD_WARPS * 32, 0, s>>>(pp, w, h);
+    const int aligned = ((uintptr_t)src % 4 == 0) && (pitch % 4 == 0) && ((uintptr_t)dst % 2 == 0) &&
+                        (dst_pitch % 2 == 0);
+    k_pyr_down<<<grid, PD_WARPS * 32, 0, s>>>(pp, w, h, aligned);
     KR_LAUNCH_CHECK();
     return KR_OK;
 }
@@ -493,7 +521,11 @@ int krl_build_pyramids(kr_ctx *ctx, const uint8_t *prev, int64_t pp, const uint8
         q.src_pitch[0] = a->pitch[0][l]; q.src_pitch[1] = a->pitch[1][l];
         q.dst_pitch[0] = q.dst_pitch[1] = pitch;
         dim3 grid((nw + PD_WARPS * PD_VALID - 1) / (PD_WARPS * PD_VALID), (nh + PD_ROWS - 1) / PD_ROWS, 2);
-        k_pyr_down<<<grid, PD_WARPS * 32, 0, s>>>(q, a->w[l], a->h[l]);
+        int aligned = (pitch % 2 == 0);
+        for (int k = 0; k < 2; k++)
+            aligned = aligned && ((uintptr_t)q.src[k] % 4 == 0) && (q.src_pitch[k] % 4 == 0) &&
+                      ((uintptr_t)q.dst[k] % 2 == 0);
+        k_pyr_down<<<grid, PD_WARPS * 32, 0, s>>>(q, a->w[l], a->h[l], aligned);
         KR_LAUNCH_CHECK();
         levels = l + 1;
     }

@@ -291,6 +291,109 @@ k_laplacian(const T *__restrict__ img, int64_t pitch, int w, int h, const uint8_
     }
 }
 
+// K2, packed form for k = 3, 5, 7: two adjacent pixels per lane in one 32-bit
+// register (16-bit fields: the smoothed value never exceeds 255 * 2^(2(k-3)) <=
+// 65280, so packed adds cannot carry across fields).  A warp covers 64 columns;
+// every cascade stage is one shuffle + one funnel shift + one add for two pixels.
+template <typename T> struct alignas(sizeof(T) * 2) Vec2 { T a, b; };
+
+template <int K, typename T>
+__global__ void __launch_bounds__(LAP_WARPS * 32)
+k_laplacian2(const T *__restrict__ img, int64_t pitch, int w, int h, const uint8_t *__restrict__ lut,
+             const KrDevStats *__restrict__ st, int slot, int invert, uint8_t *__restrict__ out,
+             int64_t out_pitch, int aligned)
+{
+    constexpr int R = K / 2;                          // 1, 2, 3
+    constexpr int NS = K - 3;                         // [1,1] stages per dimension
+    constexpr int HL = (R + 1) / 2;                   // halo in lanes (2 columns each)
+    constexpr int VALID = 64 - 4 * HL;
+    constexpr unsigned FULL = 0xffffffffu;
+
+    float fmn = 0.f, frange = 0.f;
+    if (PixTraits<T>::is_float) {
+        float mn = kr_f32_dec_bits(st->minf_enc[slot], 0), mx = kr_f32_dec_bits(st->maxf_enc[slot], 0);
+        fmn = mn;
+        frange = (mx > mn) ? (float)((double)mx - (double)mn) : 0.f;
+    }
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int xs = (blockIdx.x * LAP_WARPS + wid) * VALID;
+    if (xs >= w) return;
+    const int ys = blockIdx.y * LAP_ROWS, ye = min(ys + LAP_ROWS, h);
+    const int cx = xs + 2 * (lane - HL);              // even column of the lane
+    const int c0 = kr_reflect101(cx, w), c1 = kr_reflect101(cx + 1, w);
+    const bool vec = aligned && (xs - 2 * HL >= 0) && (xs - 2 * HL + 64 <= w);   // whole warp inside
+    const bool lane_ok = lane >= HL && lane < 32 - HL;
+    const bool st0 = lane_ok && cx < w, st1 = lane_ok && cx + 1 < w;
+
+    auto load_raw = [&](int r, T &a, T &b) {
+        int tr = r;
+        if ((unsigned)tr >= (unsigned)h) tr = kr_reflect101(r, h);
+        const T *row = (const T *)((const char *)img + (int64_t)tr * pitch);
+        if (vec) {
+            Vec2<T> q = *reinterpret_cast<const Vec2<T> *>(row + cx);
+            a = q.a; b = q.b;
+        } else {
+            a = row[c0]; b = row[c1];
+        }
+    };
+    auto norm2 = [&](T a, T b) -> uint32_t {
+        return (uint32_t)to_u8<T>(a, lut, fmn, frange, invert) |
+               ((uint32_t)to_u8<T>(b, lut, fmn, frange, invert) << 16);
+    };
+
+    uint32_t vs[NS > 0 ? NS : 1];
+#pragma unroll
+    for (int i = 0; i < (NS > 0 ? NS : 1); i++) vs[i] = 0;
+    int e0_m2 = 0, e1_m2 = 0, e0_m1 = 0, e1_m1 = 0, s0_m1 = 0, s1_m1 = 0;
+
+    const int r_first = ys - R, r_end = ye + R;
+    T ra, rb;
+    load_raw(r_first, ra, rb);
+    uint32_t v_next = norm2(ra, rb);
+    load_raw(r_first + 1, ra, rb);
+#pragma unroll 2
+    for (int r = r_first; r < r_end; r++) {
+        uint32_t v = v_next;
+        v_next = norm2(ra, rb);
+        load_raw(r + 2, ra, rb);
+        // horizontal [1,1] cascade on the packed pair, alternating direction
+#pragma unroll
+        for (int i = 0; i < NS; i++) {
+            if (i & 1) {
+                const uint32_t pv = __shfl_up_sync(FULL, v, 1);
+                v += __funnelshift_r(pv, v, 16);          // (p(x-1), p(x))
+            } else {
+                const uint32_t nv = __shfl_down_sync(FULL, v, 1);
+                v += __funnelshift_r(v, nv, 16);          // (p(x+1), p(x+2))
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < NS; i++) {                    // vertical cascade
+            const uint32_t t = v + vs[i];
+            vs[i] = v;
+            v = t;
+        }
+        // S (packed) at row r - NS/2; unpack, E(x) = S(x-1) + S(x+1)
+        const uint32_t sp = __shfl_up_sync(FULL, v, 1), sn = __shfl_down_sync(FULL, v, 1);
+        const int s0 = (int)(v & 0xffffu), s1 = (int)(v >> 16);
+        const int e0 = (int)(sp >> 16) + s1, e1 = s0 + (int)(sn & 0xffffu);
+        const int m = r - R;
+        if (m >= ys) {
+            const int a0 = 2 * (e0_m2 + e0) - 8 * s0_m1, a1 = 2 * (e1_m2 + e1) - 8 * s1_m1;
+            const int o0 = min(255, max(0, a0)), o1 = min(255, max(0, a1));
+            uint8_t *orow = out + (int64_t)m * out_pitch + cx;
+            if (vec) {
+                if (lane_ok) *reinterpret_cast<uint16_t *>(orow) = (uint16_t)(o0 | (o1 << 8));
+            } else {
+                if (st0) orow[0] = (uint8_t)o0;
+                if (st1) orow[1] = (uint8_t)o1;
+            }
+        }
+        e0_m2 = e0_m1; e1_m2 = e1_m1; e0_m1 = e0; e1_m1 = e1;
+        s0_m1 = s0; s1_m1 = s1;
+    }
+}
+
 template <typename T>
 int launch_minmax(kr_ctx *ctx, const void *a, int64_t pa, const void *b, int64_t pb, int w, int h,
                   int slot_a, int slot_b, int has_nd_a, double nd_a, int has_nd_b, double nd_b,
@@ -331,6 +434,18 @@ template <int K, typename T>
 int launch_lap(kr_ctx *ctx, const void *img, int64_t pitch, int w, int h, int slot, int invert,
                uint8_t *out, int64_t out_pitch, cudaStream_t s)
 {
+    if (K >= 3 && K <= 7) {
+        constexpr int K2 = (K >= 3 && K <= 7) ? K : 3;
+        constexpr int HL = (K2 / 2 + 1) / 2, VALID = 64 - 4 * HL;
+        const size_t va = sizeof(T) * 2;
+        const int aligned = ((uintptr_t)img % va == 0) && (pitch % (int64_t)va == 0) &&
+                            ((uintptr_t)out % 2 == 0) && (out_pitch % 2 == 0);
+        dim3 grid((w + LAP_WARPS * VALID - 1) / (LAP_WARPS * VALID), (h + LAP_ROWS - 1) / LAP_ROWS);
+        k_laplacian2<K2, T><<<grid, LAP_WARPS * 32, 0, s>>>((const T *)img, pitch, w, h, ctx->d_lut[slot],
+                                                           ctx->d_stats, slot, invert, out, out_pitch, aligned);
+        KR_LAUNCH_CHECK();
+        return KR_OK;
+    }
     constexpr int R = (K <= 3) ? 1 : K / 2;
     constexpr int VALID = 32 - 2 * R;
     dim3 grid((w + LAP_WARPS * VALID - 1) / (LAP_WARPS * VALID), (h + LAP_ROWS - 1) / LAP_ROWS);
