@@ -1,4 +1,4 @@
-// kr_prep.cu -- K1 (min/max + auto mask + valid count), LUT build and K2
+// kr_prep.cu -- K1 (min/max + auto mask + valid count), normalisation set-up and K2
 // (uint8 normalisation fused with the integer Laplacian).
 //
 // Reference call sites replaced:
@@ -134,6 +134,65 @@ k_minmax_mask(const T *__restrict__ a, int64_t pa, const T *__restrict__ b, int6
     }
 }
 
+// K1, lean form for the common case: two uint16 rasters, 8-byte aligned rows, no
+// no-data value, auto mask wanted.  Packed 16-bit min / max (two pixels per
+// instruction), zero test by product, 4 mask bytes per store, several
+// independent 8-byte loads in flight per thread.
+__global__ void __launch_bounds__(256)
+k_minmax_mask_u16(const uint16_t *__restrict__ a, int64_t pa, const uint16_t *__restrict__ b, int64_t pb,
+                  int w, int h, uint8_t *__restrict__ mask, int64_t pm, KrDevStats *st)
+{
+    uint32_t mna = 0xffffffffu, mxa = 0u, mnb = 0xffffffffu, mxb = 0u;     // packed 2 x u16
+    unsigned cnt = 0;
+    const int nv = w >> 2;
+    for (int y = blockIdx.x; y < h; y += gridDim.x) {
+        const uint2 *ra = reinterpret_cast<const uint2 *>((const char *)a + (int64_t)y * pa);
+        const uint2 *rb = reinterpret_cast<const uint2 *>((const char *)b + (int64_t)y * pb);
+        uint32_t *rm = reinterpret_cast<uint32_t *>(mask + (int64_t)y * pm);
+#pragma unroll 4
+        for (int i = threadIdx.x; i < nv; i += 256) {
+            const uint2 qa = __ldg(ra + i), qb = __ldg(rb + i);
+            mna = __vminu2(mna, __vminu2(qa.x, qa.y)); mxa = __vmaxu2(mxa, __vmaxu2(qa.x, qa.y));
+            mnb = __vminu2(mnb, __vminu2(qb.x, qb.y)); mxb = __vmaxu2(mxb, __vmaxu2(qb.x, qb.y));
+            // pixel valid <=> a * b != 0 (16 x 16 bit products cannot wrap to zero)
+            const uint32_t m0 = ((qa.x & 0xffffu) * (qb.x & 0xffffu)) != 0u;
+            const uint32_t m1 = ((qa.x >> 16) * (qb.x >> 16)) != 0u;
+            const uint32_t m2 = ((qa.y & 0xffffu) * (qb.y & 0xffffu)) != 0u;
+            const uint32_t m3 = ((qa.y >> 16) * (qb.y >> 16)) != 0u;
+            cnt += m0 + m1 + m2 + m3;
+            rm[i] = m0 | (m1 << 8) | (m2 << 16) | (m3 << 24);
+        }
+        for (int x = (nv << 2) + threadIdx.x; x < w; x += 256) {           // row tail
+            const uint32_t va = ((const uint16_t *)ra)[x], vb = ((const uint16_t *)rb)[x];
+            mna = __vminu2(mna, va | 0xffff0000u); mxa = __vmaxu2(mxa, va);
+            mnb = __vminu2(mnb, vb | 0xffff0000u); mxb = __vmaxu2(mxb, vb);
+            const uint32_t m = (va * vb) != 0u;
+            cnt += m;
+            ((uint8_t *)rm)[x] = (uint8_t)m;
+        }
+    }
+    int mn_a = (int)min(mna & 0xffffu, mna >> 16), mx_a = (int)max(mxa & 0xffffu, mxa >> 16);
+    int mn_b = (int)min(mnb & 0xffffu, mnb >> 16), mx_b = (int)max(mxb & 0xffffu, mxb >> 16);
+    mn_a = warp_min(mn_a); mx_a = warp_max(mx_a); mn_b = warp_min(mn_b); mx_b = warp_max(mx_b);
+    for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    __shared__ int s_v[4][8];
+    __shared__ unsigned s_c[8];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (lane == 0) { s_v[0][wid] = mn_a; s_v[1][wid] = mx_a; s_v[2][wid] = mn_b; s_v[3][wid] = mx_b; s_c[wid] = cnt; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned long long c = 0;
+        for (int i = 0; i < 8; i++) {
+            mn_a = min(mn_a, s_v[0][i]); mx_a = max(mx_a, s_v[1][i]);
+            mn_b = min(mn_b, s_v[2][i]); mx_b = max(mx_b, s_v[3][i]);
+            c += s_c[i];
+        }
+        publish_minmax(st, 0, mn_a, mx_a);
+        publish_minmax(st, 1, mn_b, mx_b);
+        atomicAdd(&st->valid, c);
+    }
+}
+
 __global__ void k_reset_stats(KrDevStats *st)
 {
     if (threadIdx.x == 0 && blockIdx.x == 0) {
@@ -158,45 +217,78 @@ __global__ void k_reset_slot(KrDevStats *st, int slot)
     st->minf_enc[slot] = 0xffffffffu; st->maxf_enc[slot] = 0u;
 }
 
-// 65 536-entry table of _to_uint8 for a 16-bit (or 8-bit) raster: entry = the
-// raw bit pattern of the pixel.  float64: subtract, divide, multiply by 255
-// (each correctly rounded, never fused), truncate -- klt.py:47-48.
-__global__ void k_build_lut(const KrDevStats *st, int slot, int dtype, int invert, uint8_t *lut)
+// _to_uint8 (klt.py:47-48) for integer rasters without a table: NumPy evaluates
+//   trunc( fl64( fl64((v - mn) / (mx - mn)) * 255 ) ).
+// With d = v - mn and range = mx - mn the exact quotient 255 d / range is either an
+// integer k or at least 1/range away from one, so float64 rounding can only matter
+// when range divides 255 d: there the float64 expression yields k or k - 1.  The
+// kernels therefore use exact integer division (multiply-high by a magic
+// reciprocal + remainder fix-up) and, on a zero remainder, one bit of a 256-bit
+// exception mask that this set-up kernel fills by evaluating the float64
+// expression itself for the (<= 256) exact multiples.  Bit-identical to NumPy.
+__global__ void k_norm_setup(const KrDevStats *st, int slot, int dtype, KrNorm *norm)
 {
-    int bits = blockIdx.x * blockDim.x + threadIdx.x;
-    if (bits >= 65536) return;
-    int r;
-    if (dtype == KR_U8) {
-        r = bits & 255;                                 // uint8 input: _to_uint8 is a no-op
-    } else {
-        int v = (dtype == KR_I16) ? (int)(int16_t)(uint16_t)bits : bits;
-        int mn = st->min_i[slot], mx = st->max_i[slot];
-        r = 0;
-        if (mx > mn) {
-            double q = __ddiv_rn(__dsub_rn((double)v, (double)mn), (double)(mx - mn));
-            q = __dmul_rn(q, 255.0);
-            if (q >= 0.0 && q < 256.0) r = (int)q;      // values outside [mn, mx] never occur
-        }
+    const int k = threadIdx.x;                       // 0..255
+    int mn = 0;
+    uint32_t range = 255;
+    if (dtype != KR_U8) {
+        int lo = st->min_i[slot], hi = st->max_i[slot];
+        mn = lo;
+        range = (hi > lo) ? (uint32_t)(hi - lo) : 0u;
     }
-    if (invert) r = 255 - r;
-    lut[bits] = (uint8_t)r;
+    bool exc = false;
+    if (range > 0 && ((uint64_t)k * range) % 255u == 0) {
+        const uint32_t d = (uint32_t)(((uint64_t)k * range) / 255u);
+        double q = __ddiv_rn((double)d, (double)range);         // (v - mn) is exact
+        q = __dmul_rn(q, 255.0);
+        exc = ((int)q == k - 1);
+    }
+    const unsigned bal = __ballot_sync(0xffffffffu, exc);
+    if ((k & 31) == 0) norm[slot].exc[k >> 5] = bal;
+    if (k == 0) {
+        norm[slot].mn = mn;
+        // a flat tile (mx <= mn) maps to zeros: d is always 0, any range >= 1 works
+        const uint32_t r = range ? range : 1u;
+        uint64_t m = (0x100000000ull / r) + 1ull;
+        norm[slot].range = r;
+        norm[slot].magic = (m > 0xffffffffull) ? 0xffffffffu : (uint32_t)m;
+    }
 }
 
-// uint8 value of one raw pixel: table lookup (16/8-bit rasters, L1-resident
-// 64 KB table) or the float32 expression NumPy evaluates for float32 rasters.
-template <typename T>
-__device__ __forceinline__ int to_u8(T v, const uint8_t *__restrict__ lut, float fmn, float frange,
-                                     int invert)
+struct NormReg { int mn; uint32_t range, magic; const uint32_t *exc; };
+
+__device__ __forceinline__ NormReg load_norm(const KrNorm *norm, int slot)
 {
+    NormReg n;
+    n.mn = norm[slot].mn; n.range = norm[slot].range; n.magic = norm[slot].magic;
+    n.exc = norm[slot].exc;
+    return n;
+}
+
+// uint8 value of one raw pixel: exact integer form for 8/16-bit rasters, the
+// float32 expression NumPy evaluates for float32 rasters.
+template <typename T>
+__device__ __forceinline__ int to_u8(T v, const NormReg &n, float fmn, float frange, int invert)
+{
+    int r;
     if (PixTraits<T>::is_float) {
-        int r = 0;
+        r = 0;
         if (frange > 0.f) {
             float q = __fmul_rn(__fdiv_rn(__fsub_rn((float)v, fmn), frange), 255.0f);
             if (q >= 0.f && q < 256.f) r = (int)q;
         }
-        return invert ? 255 - r : r;
+    } else if (sizeof(T) == 1) {
+        r = (int)v;                                     // uint8 input: _to_uint8 is a no-op
+    } else {
+        const uint32_t M = (uint32_t)((int)v - n.mn) * 255u;          // < 2^24
+        uint32_t q = __umulhi(M, n.magic);                           // floor(M / range) or + 1
+        int rem = (int)(M - q * n.range);
+        if (rem < 0) { q -= 1; rem += (int)n.range; }
+        if ((uint32_t)rem >= n.range) { q += 1; rem -= (int)n.range; }
+        if (rem == 0) q -= (__ldg(n.exc + (q >> 5)) >> (q & 31)) & 1u;
+        r = (int)q;
     }
-    return __ldg(lut + (uint16_t)v);       // invert is folded into the table
+    return invert ? 255 - r : r;
 }
 
 constexpr int LAP_WARPS = 8, LAP_ROWS = 64;
@@ -213,7 +305,7 @@ constexpr int LAP_WARPS = 8, LAP_ROWS = 64;
 // memory, no block synchronisation; the normalisation is the L1-resident table.
 template <int K, typename T>
 __global__ void __launch_bounds__(LAP_WARPS * 32)
-k_laplacian(const T *__restrict__ img, int64_t pitch, int w, int h, const uint8_t *__restrict__ lut,
+k_laplacian(const T *__restrict__ img, int64_t pitch, int w, int h, const KrNorm *__restrict__ norm,
             const KrDevStats *__restrict__ st, int slot, int invert, uint8_t *__restrict__ out,
             int64_t out_pitch)
 {
@@ -228,6 +320,7 @@ k_laplacian(const T *__restrict__ img, int64_t pitch, int w, int h, const uint8_
         fmn = mn;
         frange = (mx > mn) ? (float)((double)mx - (double)mn) : 0.f;
     }
+    const NormReg nr = load_norm(norm, slot);
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int xs = (blockIdx.x * LAP_WARPS + wid) * VALID;     // first output column of the strip
     if (xs >= w) return;                                        // whole warp leaves together
@@ -250,12 +343,12 @@ k_laplacian(const T *__restrict__ img, int64_t pitch, int w, int h, const uint8_
         return *((const T *)((const char *)img + (int64_t)tr * pitch) + col);
     };
     const int r_first = ys - R, r_end = ye + R;
-    int v_next = to_u8<T>(load_raw(r_first), lut, fmn, frange, invert);
+    int v_next = to_u8<T>(load_raw(r_first), nr, fmn, frange, invert);
     T raw_next = load_raw(r_first + 1);
 #pragma unroll 2
     for (int r = r_first; r < r_end; r++) {
         int v = v_next;
-        v_next = to_u8<T>(raw_next, lut, fmn, frange, invert);
+        v_next = to_u8<T>(raw_next, nr, fmn, frange, invert);
         raw_next = load_raw(r + 2);
         // horizontal binomial cascade, alternating direction to stay centred
 #pragma unroll
@@ -299,7 +392,7 @@ template <typename T> struct alignas(sizeof(T) * 2) Vec2 { T a, b; };
 
 template <int K, typename T>
 __global__ void __launch_bounds__(LAP_WARPS * 32)
-k_laplacian2(const T *__restrict__ img, int64_t pitch, int w, int h, const uint8_t *__restrict__ lut,
+k_laplacian2(const T *__restrict__ img, int64_t pitch, int w, int h, const KrNorm *__restrict__ norm,
              const KrDevStats *__restrict__ st, int slot, int invert, uint8_t *__restrict__ out,
              int64_t out_pitch, int aligned)
 {
@@ -315,6 +408,7 @@ k_laplacian2(const T *__restrict__ img, int64_t pitch, int w, int h, const uint8
         fmn = mn;
         frange = (mx > mn) ? (float)((double)mx - (double)mn) : 0.f;
     }
+    const NormReg nr = load_norm(norm, slot);
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int xs = (blockIdx.x * LAP_WARPS + wid) * VALID;
     if (xs >= w) return;
@@ -337,8 +431,8 @@ k_laplacian2(const T *__restrict__ img, int64_t pitch, int w, int h, const uint8
         }
     };
     auto norm2 = [&](T a, T b) -> uint32_t {
-        return (uint32_t)to_u8<T>(a, lut, fmn, frange, invert) |
-               ((uint32_t)to_u8<T>(b, lut, fmn, frange, invert) << 16);
+        return (uint32_t)to_u8<T>(a, nr, fmn, frange, invert) |
+               ((uint32_t)to_u8<T>(b, nr, fmn, frange, invert) << 16);
     };
 
     uint32_t vs[NS > 0 ? NS : 1];
@@ -405,6 +499,13 @@ int launch_minmax(kr_ctx *ctx, const void *a, int64_t pa, const void *b, int64_t
     if (mask) vec = vec && ((uintptr_t)mask % 4 == 0) && (pm % 4 == 0);
     int grid = ctx->num_sms * 8;
     if (grid > h) grid = h;
+    if (vec && sizeof(T) == 2 && !PixTraits<T>::is_float && ((T)-1 > (T)0) && b && mask && !has_nd_a &&
+        !has_nd_b && slot_a == 0 && slot_b == 1) {
+        k_minmax_mask_u16<<<grid, 256, 0, s>>>((const uint16_t *)a, pa, (const uint16_t *)b, pb, w, h, mask,
+                                              pm, ctx->d_stats);
+        KR_LAUNCH_CHECK();
+        return KR_OK;
+    }
     if (vec)
         k_minmax_mask<T, true><<<grid, 256, 0, s>>>((const T *)a, pa, (const T *)b, pb, w, h, slot_a,
                                                    slot_b, has_nd_a, nd_a, has_nd_b, nd_b, mask, pm,
@@ -441,7 +542,7 @@ int launch_lap(kr_ctx *ctx, const void *img, int64_t pitch, int w, int h, int sl
         const int aligned = ((uintptr_t)img % va == 0) && (pitch % (int64_t)va == 0) &&
                             ((uintptr_t)out % 2 == 0) && (out_pitch % 2 == 0);
         dim3 grid((w + LAP_WARPS * VALID - 1) / (LAP_WARPS * VALID), (h + LAP_ROWS - 1) / LAP_ROWS);
-        k_laplacian2<K2, T><<<grid, LAP_WARPS * 32, 0, s>>>((const T *)img, pitch, w, h, ctx->d_lut[slot],
+        k_laplacian2<K2, T><<<grid, LAP_WARPS * 32, 0, s>>>((const T *)img, pitch, w, h, ctx->d_norm,
                                                            ctx->d_stats, slot, invert, out, out_pitch, aligned);
         KR_LAUNCH_CHECK();
         return KR_OK;
@@ -449,7 +550,7 @@ int launch_lap(kr_ctx *ctx, const void *img, int64_t pitch, int w, int h, int sl
     constexpr int R = (K <= 3) ? 1 : K / 2;
     constexpr int VALID = 32 - 2 * R;
     dim3 grid((w + LAP_WARPS * VALID - 1) / (LAP_WARPS * VALID), (h + LAP_ROWS - 1) / LAP_ROWS);
-    k_laplacian<K, T><<<grid, LAP_WARPS * 32, 0, s>>>((const T *)img, pitch, w, h, ctx->d_lut[slot],
+    k_laplacian<K, T><<<grid, LAP_WARPS * 32, 0, s>>>((const T *)img, pitch, w, h, ctx->d_norm,
                                                      ctx->d_stats, slot, invert, out, out_pitch);
     KR_LAUNCH_CHECK();
     return KR_OK;
@@ -503,7 +604,7 @@ int krl_laplacian(kr_ctx *ctx, const void *img, int64_t pitch, int dtype, int w,
 {
     if (slot < 0 || slot > 2) return kr_set_error(KR_ERR_INVALID, "bad min/max slot %d", slot);
     if (dtype != KR_F32) {
-        k_build_lut<<<65536 / 256, 256, 0, s>>>(ctx->d_stats, slot, dtype, invert, ctx->d_lut[slot]);
+        k_norm_setup<<<1, 256, 0, s>>>(ctx->d_stats, slot, dtype, ctx->d_norm);
         KR_LAUNCH_CHECK();
     }
     switch (dtype) {
