@@ -32,7 +32,7 @@ WORKLOAD = "s2_b04_10980x10980_pair_klt_zncc_default_config"
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
     ap.add_argument("--size", type=int, default=S2, help="scene side (default: the S2 10 m band)")
@@ -158,7 +158,7 @@ class ClockSampler(threading.Thread):
                         self.reasons.add(k)
             except Exception:  # noqa: BLE001
                 pass
-            time.sleep(0.05)
+            time.sleep(0.02)
 
     def summary(self):
         med = float(np.median(self.samples)) if self.samples else None
@@ -225,12 +225,12 @@ def cuda_arm(args):
         mon, ref = scenes[i % len(scenes)]
         return sm.match_device(mon, ref, None, collect=True)
 
+    sampler = ClockSampler(local)          # NVML is initialised before the timed region
     for i in range(args.warmup):
         step(i)
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
-    sampler = ClockSampler(local)
     sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()

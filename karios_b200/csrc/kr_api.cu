@@ -145,7 +145,7 @@ KR_API int kr_ctx_create(int device, int max_w, int max_h, int max_corners, kr_c
     int rc = KR_OK;
 #define A(expr) if (rc == KR_OK) rc = (expr)
     A(dev_alloc(&c->d_stats, 1));
-    A(dev_alloc(&c->d_norm, 3));
+    for (int i = 0; i < 3; i++) A(dev_alloc(&c->d_lut[i], 65536));
     A(dev_alloc(&c->d_cand, c->cand_cap));
     A(dev_alloc(&c->d_keys_a, c->cand_cap));
     A(dev_alloc(&c->d_keys_b, c->cand_cap));
@@ -196,7 +196,7 @@ KR_API void kr_ctx_destroy(kr_ctx *c)
 {
     if (!c) return;
     cudaFree(c->d_stats);
-    cudaFree(c->d_norm);
+    for (int i = 0; i < 3; i++) cudaFree(c->d_lut[i]);
     cudaFree(c->d_cand); cudaFree(c->d_keys_a); cudaFree(c->d_keys_b); cudaFree(c->d_hist);
     cudaFree(c->d_xy); cudaFree(c->d_state); cudaFree(c->d_next); cudaFree(c->d_cell_head);
     cudaFree(c->d_mask); cudaFree(c->d_lap[0]); cudaFree(c->d_lap[1]);

@@ -29,21 +29,13 @@ struct KrDevStats {
     uint32_t pad[3];
 };
 
-// exact-integer form of _to_uint8 for one raster (see k_norm_setup)
-struct KrNorm {
-    int32_t mn;
-    uint32_t range, magic;
-    uint32_t exc[8];
-    uint32_t pad;
-};
-
 struct kr_ctx {
     int device, num_sms;
     int max_w, max_h, max_corners;
     int64_t cand_cap;       // capacity of the candidate / key lists
     int64_t corner_cap;     // capacity of corner-sized arrays
     KrDevStats *d_stats;
-    struct KrNorm *d_norm;  // _to_uint8 parameters of slots a, b, scratch (kr_prep.cu)
+    uint8_t *d_lut[3];      // 65536-entry uint8 tables (slot a, b, scratch)
     uint64_t *d_cand;       // K3 output: (float bits << 32) | (y*W + x)
     uint64_t *d_keys_a;     // selected keys / sort ping
     uint64_t *d_keys_b;     // accepted keys / sort pong

@@ -39,25 +39,29 @@ struct PyrPair {
 // shuffles of the packed word, the horizontal 5-tap sums are two dp4a, the five
 // vertical taps slide through registers as packed 16-bit pairs (two new input
 // rows per output row).  No shared memory.
-__device__ __forceinline__ uint32_t pd_hrow(const uint8_t *__restrict__ src, int64_t sp, int w, int h, int r,
+__device__ __forceinline__ uint32_t pd_load(const uint8_t *__restrict__ src, int64_t sp, int w, int h, int r,
                                             int cx, bool vec, const int *tc)
 {
-    constexpr unsigned FULL = 0xffffffffu;
     int tr = r;
     if ((unsigned)tr >= (unsigned)h) tr = kr_reflect101(r, h);
     const uint8_t *row = src + (int64_t)tr * sp;
-    uint32_t cur;
-    if (vec) cur = __ldg(reinterpret_cast<const uint32_t *>(row + cx));
-    else
-        cur = (uint32_t)__ldg(row + tc[0]) | ((uint32_t)__ldg(row + tc[1]) << 8) |
-              ((uint32_t)__ldg(row + tc[2]) << 16) | ((uint32_t)__ldg(row + tc[3]) << 24);
+    if (vec) return __ldg(reinterpret_cast<const uint32_t *>(row + cx));
+    return (uint32_t)__ldg(row + tc[0]) | ((uint32_t)__ldg(row + tc[1]) << 8) |
+           ((uint32_t)__ldg(row + tc[2]) << 16) | ((uint32_t)__ldg(row + tc[3]) << 24);
+}
+
+// horizontal 5-tap sums of the lane's two outputs from its word (a0..a3) and the
+// neighbour lanes' words, packed as two 16-bit fields (each <= 4080)
+__device__ __forceinline__ uint32_t pd_hsum(uint32_t cur)
+{
+    constexpr unsigned FULL = 0xffffffffu;
     const uint32_t lw = __shfl_up_sync(FULL, cur, 1), rw = __shfl_down_sync(FULL, cur, 1);
     // output 0 (input centre a0): L.a2 + 4 L.a3 + 6 a0 + 4 a1 + a2
     const uint32_t w0 = __byte_perm(lw, cur, 0x5432);            // bytes (L.a2, L.a3, a0, a1)
     const uint32_t h0 = __dp4a(w0, 0x04060401u, (cur >> 16) & 255u);
     // output 1 (input centre a2): a0 + 4 a1 + 6 a2 + 4 a3 + R.a0
     const uint32_t h1 = __dp4a(cur, 0x04060401u, rw & 255u);
-    return h0 | (h1 << 16);                                     // each <= 4080
+    return h0 | (h1 << 16);
 }
 
 __global__ void __launch_bounds__(PD_WARPS * 32) k_pyr_down(PyrPair pp, int w, int h, int aligned)
@@ -79,15 +83,7 @@ __global__ void __launch_bounds__(PD_WARPS * 32) k_pyr_down(PyrPair pp, int w, i
     const bool lane_ok = lane >= 1 && lane <= 30;
     const bool st0 = lane_ok && ox < dw, st1 = lane_ok && ox + 1 < dw;
 
-    const int r = 2 * oys - 2;
-    uint32_t h0 = pd_hrow(src, sp, w, h, r, cx, vec, tc), h1 = pd_hrow(src, sp, w, h, r + 1, cx, vec, tc),
-             h2 = pd_hrow(src, sp, w, h, r + 2, cx, vec, tc);
-#pragma unroll 2
-    for (int oy = oys; oy < oye; oy++) {
-        const uint32_t h3 = pd_hrow(src, sp, w, h, 2 * oy + 1, cx, vec, tc),
-                       h4 = pd_hrow(src, sp, w, h, 2 * oy + 2, cx, vec, tc);
-        // packed 16-bit pairs: (h0 + h4) + 4 (h1 + h3) + 6 h2 <= 16 * 4080 = 65280 per field
-        const uint32_t acc = h0 + h4 + 4u * (h1 + h3) + 6u * h2 + 0x00800080u;
+    auto store = [&](int oy, uint32_t acc) {
         const uint32_t o0 = (acc >> 8) & 255u, o1 = acc >> 24;
         uint8_t *orow = dst + (int64_t)oy * dp + ox;
         if (vec) {
@@ -96,7 +92,29 @@ __global__ void __launch_bounds__(PD_WARPS * 32) k_pyr_down(PyrPair pp, int w, i
             if (st0) orow[0] = (uint8_t)o0;
             if (st1) orow[1] = (uint8_t)o1;
         }
-        h0 = h2; h1 = h3; h2 = h4;
+    };
+
+    const int r0 = 2 * oys - 2;
+    uint32_t h0 = pd_hsum(pd_load(src, sp, w, h, r0, cx, vec, tc));
+    uint32_t h1 = pd_hsum(pd_load(src, sp, w, h, r0 + 1, cx, vec, tc));
+    uint32_t h2 = pd_hsum(pd_load(src, sp, w, h, r0 + 2, cx, vec, tc));
+    // four input rows (two output rows) are requested one iteration ahead
+    uint32_t n0 = pd_load(src, sp, w, h, r0 + 3, cx, vec, tc), n1 = pd_load(src, sp, w, h, r0 + 4, cx, vec, tc),
+             n2 = pd_load(src, sp, w, h, r0 + 5, cx, vec, tc), n3 = pd_load(src, sp, w, h, r0 + 6, cx, vec, tc);
+    for (int oy = oys; oy < oye; oy += 2) {
+        const uint32_t c0 = n0, c1 = n1, c2 = n2, c3 = n3;
+        if (oy + 2 < oye) {
+            n0 = pd_load(src, sp, w, h, 2 * oy + 5, cx, vec, tc);
+            n1 = pd_load(src, sp, w, h, 2 * oy + 6, cx, vec, tc);
+            n2 = pd_load(src, sp, w, h, 2 * oy + 7, cx, vec, tc);
+            n3 = pd_load(src, sp, w, h, 2 * oy + 8, cx, vec, tc);
+        }
+        // packed 16-bit pairs: (h0 + h4) + 4 (h1 + h3) + 6 h2 <= 16 * 4080 = 65280 per field
+        const uint32_t h3 = pd_hsum(c0), h4 = pd_hsum(c1);
+        store(oy, h0 + h4 + 4u * (h1 + h3) + 6u * h2 + 0x00800080u);
+        const uint32_t h5 = pd_hsum(c2), h6 = pd_hsum(c3);       // shuffles: all lanes take part
+        if (oy + 1 < oye) store(oy + 1, h2 + h6 + 4u * (h3 + h5) + 6u * h4 + 0x00800080u);
+        h0 = h4; h1 = h5; h2 = h6;
     }
 }
 

@@ -1,4 +1,4 @@
-// kr_prep.cu -- K1 (min/max + auto mask + valid count), normalisation set-up and K2
+// kr_prep.cu -- K1 (min/max + auto mask + valid count), LUT build and K2
 // (uint8 normalisation fused with the integer Laplacian).
 //
 // Reference call sites replaced:
@@ -217,78 +217,45 @@ __global__ void k_reset_slot(KrDevStats *st, int slot)
     st->minf_enc[slot] = 0xffffffffu; st->maxf_enc[slot] = 0u;
 }
 
-// _to_uint8 (klt.py:47-48) for integer rasters without a table: NumPy evaluates
-//   trunc( fl64( fl64((v - mn) / (mx - mn)) * 255 ) ).
-// With d = v - mn and range = mx - mn the exact quotient 255 d / range is either an
-// integer k or at least 1/range away from one, so float64 rounding can only matter
-// when range divides 255 d: there the float64 expression yields k or k - 1.  The
-// kernels therefore use exact integer division (multiply-high by a magic
-// reciprocal + remainder fix-up) and, on a zero remainder, one bit of a 256-bit
-// exception mask that this set-up kernel fills by evaluating the float64
-// expression itself for the (<= 256) exact multiples.  Bit-identical to NumPy.
-__global__ void k_norm_setup(const KrDevStats *st, int slot, int dtype, KrNorm *norm)
+// 65 536-entry table of _to_uint8 for a 16-bit (or 8-bit) raster: entry = the
+// raw bit pattern of the pixel.  float64: subtract, divide, multiply by 255
+// (each correctly rounded, never fused), truncate -- klt.py:47-48.
+__global__ void k_build_lut(const KrDevStats *st, int slot, int dtype, int invert, uint8_t *lut)
 {
-    const int k = threadIdx.x;                       // 0..255
-    int mn = 0;
-    uint32_t range = 255;
-    if (dtype != KR_U8) {
-        int lo = st->min_i[slot], hi = st->max_i[slot];
-        mn = lo;
-        range = (hi > lo) ? (uint32_t)(hi - lo) : 0u;
-    }
-    bool exc = false;
-    if (range > 0 && ((uint64_t)k * range) % 255u == 0) {
-        const uint32_t d = (uint32_t)(((uint64_t)k * range) / 255u);
-        double q = __ddiv_rn((double)d, (double)range);         // (v - mn) is exact
-        q = __dmul_rn(q, 255.0);
-        exc = ((int)q == k - 1);
-    }
-    const unsigned bal = __ballot_sync(0xffffffffu, exc);
-    if ((k & 31) == 0) norm[slot].exc[k >> 5] = bal;
-    if (k == 0) {
-        norm[slot].mn = mn;
-        // a flat tile (mx <= mn) maps to zeros: d is always 0, any range >= 1 works
-        const uint32_t r = range ? range : 1u;
-        uint64_t m = (0x100000000ull / r) + 1ull;
-        norm[slot].range = r;
-        norm[slot].magic = (m > 0xffffffffull) ? 0xffffffffu : (uint32_t)m;
-    }
-}
-
-struct NormReg { int mn; uint32_t range, magic; const uint32_t *exc; };
-
-__device__ __forceinline__ NormReg load_norm(const KrNorm *norm, int slot)
-{
-    NormReg n;
-    n.mn = norm[slot].mn; n.range = norm[slot].range; n.magic = norm[slot].magic;
-    n.exc = norm[slot].exc;
-    return n;
-}
-
-// uint8 value of one raw pixel: exact integer form for 8/16-bit rasters, the
-// float32 expression NumPy evaluates for float32 rasters.
-template <typename T>
-__device__ __forceinline__ int to_u8(T v, const NormReg &n, float fmn, float frange, int invert)
-{
+    int bits = blockIdx.x * blockDim.x + threadIdx.x;
+    if (bits >= 65536) return;
     int r;
-    if (PixTraits<T>::is_float) {
+    if (dtype == KR_U8) {
+        r = bits & 255;                                 // uint8 input: _to_uint8 is a no-op
+    } else {
+        int v = (dtype == KR_I16) ? (int)(int16_t)(uint16_t)bits : bits;
+        int mn = st->min_i[slot], mx = st->max_i[slot];
         r = 0;
+        if (mx > mn) {
+            double q = __ddiv_rn(__dsub_rn((double)v, (double)mn), (double)(mx - mn));
+            q = __dmul_rn(q, 255.0);
+            if (q >= 0.0 && q < 256.0) r = (int)q;      // values outside [mn, mx] never occur
+        }
+    }
+    if (invert) r = 255 - r;
+    lut[bits] = (uint8_t)r;
+}
+
+// uint8 value of one raw pixel: table lookup (16/8-bit rasters, L1-resident
+// 64 KB table) or the float32 expression NumPy evaluates for float32 rasters.
+template <typename T>
+__device__ __forceinline__ int to_u8(T v, const uint8_t *__restrict__ lut, float fmn, float frange,
+                                     int invert)
+{
+    if (PixTraits<T>::is_float) {
+        int r = 0;
         if (frange > 0.f) {
             float q = __fmul_rn(__fdiv_rn(__fsub_rn((float)v, fmn), frange), 255.0f);
             if (q >= 0.f && q < 256.f) r = (int)q;
         }
-    } else if (sizeof(T) == 1) {
-        r = (int)v;                                     // uint8 input: _to_uint8 is a no-op
-    } else {
-        const uint32_t M = (uint32_t)((int)v - n.mn) * 255u;          // < 2^24
-        uint32_t q = __umulhi(M, n.magic);                           // floor(M / range) or + 1
-        int rem = (int)(M - q * n.range);
-        if (rem < 0) { q -= 1; rem += (int)n.range; }
-        if ((uint32_t)rem >= n.range) { q += 1; rem -= (int)n.range; }
-        if (rem == 0) q -= (__ldg(n.exc + (q >> 5)) >> (q & 31)) & 1u;
-        r = (int)q;
+        return invert ? 255 - r : r;
     }
-    return invert ? 255 - r : r;
+    return __ldg(lut + (uint16_t)v);       // invert is folded into the table
 }
 
 constexpr int LAP_WARPS = 8, LAP_ROWS = 64;
@@ -305,7 +272,7 @@ constexpr int LAP_WARPS = 8, LAP_ROWS = 64;
 // memory, no block synchronisation; the normalisation is the L1-resident table.
 template <int K, typename T>
 __global__ void __launch_bounds__(LAP_WARPS * 32)
-k_laplacian(const T *__restrict__ img, int64_t pitch, int w, int h, const KrNorm *__restrict__ norm,
+k_laplacian(const T *__restrict__ img, int64_t pitch, int w, int h, const uint8_t *__restrict__ lut,
             const KrDevStats *__restrict__ st, int slot, int invert, uint8_t *__restrict__ out,
             int64_t out_pitch)
 {
@@ -320,7 +287,6 @@ k_laplacian(const T *__restrict__ img, int64_t pitch, int w, int h, const KrNorm
         fmn = mn;
         frange = (mx > mn) ? (float)((double)mx - (double)mn) : 0.f;
     }
-    const NormReg nr = load_norm(norm, slot);
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int xs = (blockIdx.x * LAP_WARPS + wid) * VALID;     // first output column of the strip
     if (xs >= w) return;                                        // whole warp leaves together
@@ -343,12 +309,12 @@ k_laplacian(const T *__restrict__ img, int64_t pitch, int w, int h, const KrNorm
         return *((const T *)((const char *)img + (int64_t)tr * pitch) + col);
     };
     const int r_first = ys - R, r_end = ye + R;
-    int v_next = to_u8<T>(load_raw(r_first), nr, fmn, frange, invert);
+    int v_next = to_u8<T>(load_raw(r_first), lut, fmn, frange, invert);
     T raw_next = load_raw(r_first + 1);
 #pragma unroll 2
     for (int r = r_first; r < r_end; r++) {
         int v = v_next;
-        v_next = to_u8<T>(raw_next, nr, fmn, frange, invert);
+        v_next = to_u8<T>(raw_next, lut, fmn, frange, invert);
         raw_next = load_raw(r + 2);
         // horizontal binomial cascade, alternating direction to stay centred
 #pragma unroll
@@ -392,7 +358,7 @@ template <typename T> struct alignas(sizeof(T) * 2) Vec2 { T a, b; };
 
 template <int K, typename T>
 __global__ void __launch_bounds__(LAP_WARPS * 32)
-k_laplacian2(const T *__restrict__ img, int64_t pitch, int w, int h, const KrNorm *__restrict__ norm,
+k_laplacian2(const T *__restrict__ img, int64_t pitch, int w, int h, const uint8_t *__restrict__ lut,
              const KrDevStats *__restrict__ st, int slot, int invert, uint8_t *__restrict__ out,
              int64_t out_pitch, int aligned)
 {
@@ -408,7 +374,6 @@ k_laplacian2(const T *__restrict__ img, int64_t pitch, int w, int h, const KrNor
         fmn = mn;
         frange = (mx > mn) ? (float)((double)mx - (double)mn) : 0.f;
     }
-    const NormReg nr = load_norm(norm, slot);
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int xs = (blockIdx.x * LAP_WARPS + wid) * VALID;
     if (xs >= w) return;
@@ -419,20 +384,21 @@ k_laplacian2(const T *__restrict__ img, int64_t pitch, int w, int h, const KrNor
     const bool lane_ok = lane >= HL && lane < 32 - HL;
     const bool st0 = lane_ok && cx < w, st1 = lane_ok && cx + 1 < w;
 
-    auto load_raw = [&](int r, T &a, T &b) {
+    auto load_raw = [&](int r) -> Vec2<T> {
         int tr = r;
         if ((unsigned)tr >= (unsigned)h) tr = kr_reflect101(r, h);
         const T *row = (const T *)((const char *)img + (int64_t)tr * pitch);
+        Vec2<T> q;
         if (vec) {
-            Vec2<T> q = *reinterpret_cast<const Vec2<T> *>(row + cx);
-            a = q.a; b = q.b;
+            q = *reinterpret_cast<const Vec2<T> *>(row + cx);
         } else {
-            a = row[c0]; b = row[c1];
+            q.a = row[c0]; q.b = row[c1];
         }
+        return q;
     };
-    auto norm2 = [&](T a, T b) -> uint32_t {
-        return (uint32_t)to_u8<T>(a, nr, fmn, frange, invert) |
-               ((uint32_t)to_u8<T>(b, nr, fmn, frange, invert) << 16);
+    auto norm2 = [&](const Vec2<T> &q) -> uint32_t {
+        return (uint32_t)to_u8<T>(q.a, lut, fmn, frange, invert) |
+               ((uint32_t)to_u8<T>(q.b, lut, fmn, frange, invert) << 16);
     };
 
     uint32_t vs[NS > 0 ? NS : 1];
@@ -440,16 +406,20 @@ k_laplacian2(const T *__restrict__ img, int64_t pitch, int w, int h, const KrNor
     for (int i = 0; i < (NS > 0 ? NS : 1); i++) vs[i] = 0;
     int e0_m2 = 0, e1_m2 = 0, e0_m1 = 0, e1_m1 = 0, s0_m1 = 0, s1_m1 = 0;
 
+    // raw pixels are requested PF rows ahead (several independent loads in flight per
+    // lane); the loop is unrolled by PF so the prefetch ring lives in registers
+    constexpr int PF = 4;
     const int r_first = ys - R, r_end = ye + R;
-    T ra, rb;
-    load_raw(r_first, ra, rb);
-    uint32_t v_next = norm2(ra, rb);
-    load_raw(r_first + 1, ra, rb);
-#pragma unroll 2
-    for (int r = r_first; r < r_end; r++) {
-        uint32_t v = v_next;
-        v_next = norm2(ra, rb);
-        load_raw(r + 2, ra, rb);
+    Vec2<T> raw[PF];
+#pragma unroll
+    for (int u = 0; u < PF; u++) raw[u] = load_raw(r_first + u);
+    for (int rb = r_first; rb < r_end; rb += PF) {
+#pragma unroll
+      for (int u = 0; u < PF; u++) {
+        const int r = rb + u;
+        if (r >= r_end) break;
+        uint32_t v = norm2(raw[u]);
+        raw[u] = load_raw(r + PF);
         // horizontal [1,1] cascade on the packed pair, alternating direction
 #pragma unroll
         for (int i = 0; i < NS; i++) {
@@ -485,6 +455,7 @@ k_laplacian2(const T *__restrict__ img, int64_t pitch, int w, int h, const KrNor
         }
         e0_m2 = e0_m1; e1_m2 = e1_m1; e0_m1 = e0; e1_m1 = e1;
         s0_m1 = s0; s1_m1 = s1;
+      }
     }
 }
 
@@ -542,7 +513,7 @@ int launch_lap(kr_ctx *ctx, const void *img, int64_t pitch, int w, int h, int sl
         const int aligned = ((uintptr_t)img % va == 0) && (pitch % (int64_t)va == 0) &&
                             ((uintptr_t)out % 2 == 0) && (out_pitch % 2 == 0);
         dim3 grid((w + LAP_WARPS * VALID - 1) / (LAP_WARPS * VALID), (h + LAP_ROWS - 1) / LAP_ROWS);
-        k_laplacian2<K2, T><<<grid, LAP_WARPS * 32, 0, s>>>((const T *)img, pitch, w, h, ctx->d_norm,
+        k_laplacian2<K2, T><<<grid, LAP_WARPS * 32, 0, s>>>((const T *)img, pitch, w, h, ctx->d_lut[slot],
                                                            ctx->d_stats, slot, invert, out, out_pitch, aligned);
         KR_LAUNCH_CHECK();
         return KR_OK;
@@ -550,7 +521,7 @@ int launch_lap(kr_ctx *ctx, const void *img, int64_t pitch, int w, int h, int sl
     constexpr int R = (K <= 3) ? 1 : K / 2;
     constexpr int VALID = 32 - 2 * R;
     dim3 grid((w + LAP_WARPS * VALID - 1) / (LAP_WARPS * VALID), (h + LAP_ROWS - 1) / LAP_ROWS);
-    k_laplacian<K, T><<<grid, LAP_WARPS * 32, 0, s>>>((const T *)img, pitch, w, h, ctx->d_norm,
+    k_laplacian<K, T><<<grid, LAP_WARPS * 32, 0, s>>>((const T *)img, pitch, w, h, ctx->d_lut[slot],
                                                      ctx->d_stats, slot, invert, out, out_pitch);
     KR_LAUNCH_CHECK();
     return KR_OK;
@@ -604,7 +575,7 @@ int krl_laplacian(kr_ctx *ctx, const void *img, int64_t pitch, int dtype, int w,
 {
     if (slot < 0 || slot > 2) return kr_set_error(KR_ERR_INVALID, "bad min/max slot %d", slot);
     if (dtype != KR_F32) {
-        k_norm_setup<<<1, 256, 0, s>>>(ctx->d_stats, slot, dtype, ctx->d_norm);
+        k_build_lut<<<65536 / 256, 256, 0, s>>>(ctx->d_stats, slot, dtype, invert, ctx->d_lut[slot]);
         KR_LAUNCH_CHECK();
     }
     switch (dtype) {
