@@ -39,17 +39,6 @@ struct PyrPair {
 // shuffles of the packed word, the horizontal 5-tap sums are two dp4a, the five
 // vertical taps slide through registers as packed 16-bit pairs (two new input
 // rows per output row).  No shared memory.
-__device__ __forceinline__ uint32_t pd_load(const uint8_t *__restrict__ src, int64_t sp, int w, int h, int r,
-                                            int cx, bool vec, const int *tc)
-{
-    int tr = r;
-    if ((unsigned)tr >= (unsigned)h) tr = kr_reflect101(r, h);
-    const uint8_t *row = src + (int64_t)tr * sp;
-    if (vec) return __ldg(reinterpret_cast<const uint32_t *>(row + cx));
-    return (uint32_t)__ldg(row + tc[0]) | ((uint32_t)__ldg(row + tc[1]) << 8) |
-           ((uint32_t)__ldg(row + tc[2]) << 16) | ((uint32_t)__ldg(row + tc[3]) << 24);
-}
-
 // horizontal 5-tap sums of the lane's two outputs from its word (a0..a3) and the
 // neighbour lanes' words, packed as two 16-bit fields (each <= 4080)
 __device__ __forceinline__ uint32_t pd_hsum(uint32_t cur)
@@ -64,6 +53,63 @@ __device__ __forceinline__ uint32_t pd_hsum(uint32_t cur)
     return h0 | (h1 << 16);
 }
 
+// FAST: all 128 input columns of the warp and all input rows it touches are inside
+// the image and the planes are aligned (running pointers, 32-bit loads, 16-bit stores).
+template <bool FAST>
+__device__ __forceinline__ void pyr_down_body(const uint8_t *__restrict__ src, int64_t sp,
+                                              uint8_t *__restrict__ dst, int64_t dp, int w, int h, int dw,
+                                              int xs, int oys, int oye, int lane)
+{
+    const int ox = xs + 2 * (lane - 1);                            // two outputs: ox, ox + 1
+    const int cx = 2 * ox;                                         // four inputs: cx .. cx + 3
+    int tc[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++) tc[j] = FAST ? cx + j : kr_reflect101(cx + j, w);
+    const bool lane_ok = lane >= 1 && lane <= 30;
+    const bool st0 = lane_ok && ox < dw, st1 = lane_ok && ox + 1 < dw;
+    const int r0 = 2 * oys - 2;
+    const uint8_t *pl = src + (int64_t)r0 * sp + cx;               // FAST only
+    int r_load = r0;
+    auto load_next = [&]() -> uint32_t {
+        if (FAST) {
+            const uint32_t v = __ldg(reinterpret_cast<const uint32_t *>(pl));
+            pl += sp;
+            return v;
+        }
+        int tr = r_load;
+        if ((unsigned)tr >= (unsigned)h) tr = kr_reflect101(r_load, h);
+        r_load++;
+        const uint8_t *row = src + (int64_t)tr * sp;
+        return (uint32_t)__ldg(row + tc[0]) | ((uint32_t)__ldg(row + tc[1]) << 8) |
+               ((uint32_t)__ldg(row + tc[2]) << 16) | ((uint32_t)__ldg(row + tc[3]) << 24);
+    };
+    uint8_t *po = dst + (int64_t)oys * dp + ox;
+    auto store_next = [&](uint32_t acc) {
+        const uint32_t o0 = (acc >> 8) & 255u, o1 = acc >> 24;
+        if (FAST) {
+            if (lane_ok) *reinterpret_cast<uint16_t *>(po) = (uint16_t)(o0 | (o1 << 8));
+        } else {
+            if (st0) po[0] = (uint8_t)o0;
+            if (st1) po[1] = (uint8_t)o1;
+        }
+        po += dp;
+    };
+
+    uint32_t h0 = pd_hsum(load_next()), h1 = pd_hsum(load_next()), h2 = pd_hsum(load_next());
+    // four input rows (two output rows) are requested one iteration ahead
+    uint32_t n0 = load_next(), n1 = load_next(), n2 = load_next(), n3 = load_next();
+    for (int oy = oys; oy < oye; oy += 2) {
+        const uint32_t c0 = n0, c1 = n1, c2 = n2, c3 = n3;
+        if (oy + 2 < oye) { n0 = load_next(); n1 = load_next(); n2 = load_next(); n3 = load_next(); }
+        // packed 16-bit pairs: (h0 + h4) + 4 (h1 + h3) + 6 h2 <= 16 * 4080 = 65280 per field
+        const uint32_t h3 = pd_hsum(c0), h4 = pd_hsum(c1);
+        store_next(h0 + h4 + 4u * (h1 + h3) + 6u * h2 + 0x00800080u);
+        const uint32_t h5 = pd_hsum(c2), h6 = pd_hsum(c3);       // shuffles: all lanes take part
+        if (oy + 1 < oye) store_next(h2 + h6 + 4u * (h3 + h5) + 6u * h4 + 0x00800080u);
+        h0 = h4; h1 = h5; h2 = h6;
+    }
+}
+
 __global__ void __launch_bounds__(PD_WARPS * 32) k_pyr_down(PyrPair pp, int w, int h, int aligned)
 {
     const uint8_t *__restrict__ src = pp.src[blockIdx.z];
@@ -74,48 +120,10 @@ __global__ void __launch_bounds__(PD_WARPS * 32) k_pyr_down(PyrPair pp, int w, i
     const int xs = (blockIdx.x * PD_WARPS + wid) * PD_VALID;      // first output column of the warp
     if (xs >= dw) return;
     const int oys = blockIdx.y * PD_ROWS, oye = min(oys + PD_ROWS, dh);
-    const int ox = xs + 2 * (lane - 1);                            // two outputs: ox, ox + 1
-    const int cx = 2 * ox;                                         // four inputs: cx .. cx + 3
-    int tc[4];
-#pragma unroll
-    for (int j = 0; j < 4; j++) tc[j] = kr_reflect101(cx + j, w);
-    const bool vec = aligned && (2 * xs - 4 >= 0) && (2 * xs - 4 + 128 <= w);
-    const bool lane_ok = lane >= 1 && lane <= 30;
-    const bool st0 = lane_ok && ox < dw, st1 = lane_ok && ox + 1 < dw;
-
-    auto store = [&](int oy, uint32_t acc) {
-        const uint32_t o0 = (acc >> 8) & 255u, o1 = acc >> 24;
-        uint8_t *orow = dst + (int64_t)oy * dp + ox;
-        if (vec) {
-            if (lane_ok) *reinterpret_cast<uint16_t *>(orow) = (uint16_t)(o0 | (o1 << 8));
-        } else {
-            if (st0) orow[0] = (uint8_t)o0;
-            if (st1) orow[1] = (uint8_t)o1;
-        }
-    };
-
-    const int r0 = 2 * oys - 2;
-    uint32_t h0 = pd_hsum(pd_load(src, sp, w, h, r0, cx, vec, tc));
-    uint32_t h1 = pd_hsum(pd_load(src, sp, w, h, r0 + 1, cx, vec, tc));
-    uint32_t h2 = pd_hsum(pd_load(src, sp, w, h, r0 + 2, cx, vec, tc));
-    // four input rows (two output rows) are requested one iteration ahead
-    uint32_t n0 = pd_load(src, sp, w, h, r0 + 3, cx, vec, tc), n1 = pd_load(src, sp, w, h, r0 + 4, cx, vec, tc),
-             n2 = pd_load(src, sp, w, h, r0 + 5, cx, vec, tc), n3 = pd_load(src, sp, w, h, r0 + 6, cx, vec, tc);
-    for (int oy = oys; oy < oye; oy += 2) {
-        const uint32_t c0 = n0, c1 = n1, c2 = n2, c3 = n3;
-        if (oy + 2 < oye) {
-            n0 = pd_load(src, sp, w, h, 2 * oy + 5, cx, vec, tc);
-            n1 = pd_load(src, sp, w, h, 2 * oy + 6, cx, vec, tc);
-            n2 = pd_load(src, sp, w, h, 2 * oy + 7, cx, vec, tc);
-            n3 = pd_load(src, sp, w, h, 2 * oy + 8, cx, vec, tc);
-        }
-        // packed 16-bit pairs: (h0 + h4) + 4 (h1 + h3) + 6 h2 <= 16 * 4080 = 65280 per field
-        const uint32_t h3 = pd_hsum(c0), h4 = pd_hsum(c1);
-        store(oy, h0 + h4 + 4u * (h1 + h3) + 6u * h2 + 0x00800080u);
-        const uint32_t h5 = pd_hsum(c2), h6 = pd_hsum(c3);       // shuffles: all lanes take part
-        if (oy + 1 < oye) store(oy + 1, h2 + h6 + 4u * (h3 + h5) + 6u * h4 + 0x00800080u);
-        h0 = h4; h1 = h5; h2 = h6;
-    }
+    const bool fast = aligned && (2 * xs - 4 >= 0) && (2 * xs - 4 + 128 <= w) && (2 * oys - 2 >= 0) &&
+                      (2 * oye + 6 <= h);
+    if (fast) pyr_down_body<true>(src, sp, dst, dp, w, h, dw, xs, oys, oye, lane);
+    else pyr_down_body<false>(src, sp, dst, dp, w, h, dw, xs, oys, oye, lane);
 }
 
 // --------------------------------------------------------------------- K6 LK

@@ -356,43 +356,39 @@ k_laplacian(const T *__restrict__ img, int64_t pitch, int w, int h, const uint8_
 // every cascade stage is one shuffle + one funnel shift + one add for two pixels.
 template <typename T> struct alignas(sizeof(T) * 2) Vec2 { T a, b; };
 
-template <int K, typename T>
-__global__ void __launch_bounds__(LAP_WARPS * 32)
-k_laplacian2(const T *__restrict__ img, int64_t pitch, int w, int h, const uint8_t *__restrict__ lut,
-             const KrDevStats *__restrict__ st, int slot, int invert, uint8_t *__restrict__ out,
-             int64_t out_pitch, int aligned)
+// FAST: every column of the warp and every row it touches (incl. the prefetch
+// distance) lies inside the image and the planes are aligned: vector loads /
+// stores through running pointers, no border arithmetic at all.
+template <int K, typename T, bool FAST>
+__device__ __forceinline__ void lap2_body(const T *__restrict__ img, int64_t pitch, int w, int h,
+                                          const uint8_t *__restrict__ lut, float fmn, float frange,
+                                          int invert, uint8_t *__restrict__ out, int64_t out_pitch,
+                                          int xs, int ys, int ye, int lane)
 {
     constexpr int R = K / 2;                          // 1, 2, 3
     constexpr int NS = K - 3;                         // [1,1] stages per dimension
     constexpr int HL = (R + 1) / 2;                   // halo in lanes (2 columns each)
-    constexpr int VALID = 64 - 4 * HL;
+    constexpr int PF = 4;                             // rows of load prefetch
     constexpr unsigned FULL = 0xffffffffu;
-
-    float fmn = 0.f, frange = 0.f;
-    if (PixTraits<T>::is_float) {
-        float mn = kr_f32_dec_bits(st->minf_enc[slot], 0), mx = kr_f32_dec_bits(st->maxf_enc[slot], 0);
-        fmn = mn;
-        frange = (mx > mn) ? (float)((double)mx - (double)mn) : 0.f;
-    }
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const int xs = (blockIdx.x * LAP_WARPS + wid) * VALID;
-    if (xs >= w) return;
-    const int ys = blockIdx.y * LAP_ROWS, ye = min(ys + LAP_ROWS, h);
     const int cx = xs + 2 * (lane - HL);              // even column of the lane
-    const int c0 = kr_reflect101(cx, w), c1 = kr_reflect101(cx + 1, w);
-    const bool vec = aligned && (xs - 2 * HL >= 0) && (xs - 2 * HL + 64 <= w);   // whole warp inside
+    const int c0 = FAST ? cx : kr_reflect101(cx, w), c1 = FAST ? cx + 1 : kr_reflect101(cx + 1, w);
     const bool lane_ok = lane >= HL && lane < 32 - HL;
     const bool st0 = lane_ok && cx < w, st1 = lane_ok && cx + 1 < w;
+    const int r_first = ys - R, r_end = ye + R;
 
-    auto load_raw = [&](int r) -> Vec2<T> {
-        int tr = r;
-        if ((unsigned)tr >= (unsigned)h) tr = kr_reflect101(r, h);
-        const T *row = (const T *)((const char *)img + (int64_t)tr * pitch);
+    const char *pl = (const char *)img + (int64_t)r_first * pitch + (int64_t)cx * sizeof(T);   // FAST only
+    int r_load = r_first;
+    auto load_next = [&]() -> Vec2<T> {
         Vec2<T> q;
-        if (vec) {
-            q = *reinterpret_cast<const Vec2<T> *>(row + cx);
+        if (FAST) {
+            q = *reinterpret_cast<const Vec2<T> *>(pl);
+            pl += pitch;
         } else {
+            int tr = r_load;
+            if ((unsigned)tr >= (unsigned)h) tr = kr_reflect101(r_load, h);
+            const T *row = (const T *)((const char *)img + (int64_t)tr * pitch);
             q.a = row[c0]; q.b = row[c1];
+            r_load++;
         }
         return q;
     };
@@ -405,58 +401,79 @@ k_laplacian2(const T *__restrict__ img, int64_t pitch, int w, int h, const uint8
 #pragma unroll
     for (int i = 0; i < (NS > 0 ? NS : 1); i++) vs[i] = 0;
     int e0_m2 = 0, e1_m2 = 0, e0_m1 = 0, e1_m1 = 0, s0_m1 = 0, s1_m1 = 0;
+    uint8_t *po = out + (int64_t)ys * out_pitch + cx;           // output row m = ys first
 
-    // raw pixels are requested PF rows ahead (several independent loads in flight per
-    // lane); the loop is unrolled by PF so the prefetch ring lives in registers
-    constexpr int PF = 4;
-    const int r_first = ys - R, r_end = ye + R;
     Vec2<T> raw[PF];
 #pragma unroll
-    for (int u = 0; u < PF; u++) raw[u] = load_raw(r_first + u);
+    for (int u = 0; u < PF; u++) raw[u] = load_next();
     for (int rb = r_first; rb < r_end; rb += PF) {
 #pragma unroll
-      for (int u = 0; u < PF; u++) {
-        const int r = rb + u;
-        if (r >= r_end) break;
-        uint32_t v = norm2(raw[u]);
-        raw[u] = load_raw(r + PF);
-        // horizontal [1,1] cascade on the packed pair, alternating direction
+        for (int u = 0; u < PF; u++) {
+            const int r = rb + u;
+            if (r >= r_end) break;
+            uint32_t v = norm2(raw[u]);
+            raw[u] = load_next();
+            // horizontal [1,1] cascade on the packed pair, alternating direction
 #pragma unroll
-        for (int i = 0; i < NS; i++) {
-            if (i & 1) {
-                const uint32_t pv = __shfl_up_sync(FULL, v, 1);
-                v += __funnelshift_r(pv, v, 16);          // (p(x-1), p(x))
-            } else {
-                const uint32_t nv = __shfl_down_sync(FULL, v, 1);
-                v += __funnelshift_r(v, nv, 16);          // (p(x+1), p(x+2))
+            for (int i = 0; i < NS; i++) {
+                if (i & 1) {
+                    const uint32_t pv = __shfl_up_sync(FULL, v, 1);
+                    v += __funnelshift_r(pv, v, 16);          // (p(x-1), p(x))
+                } else {
+                    const uint32_t nv = __shfl_down_sync(FULL, v, 1);
+                    v += __funnelshift_r(v, nv, 16);          // (p(x+1), p(x+2))
+                }
             }
-        }
 #pragma unroll
-        for (int i = 0; i < NS; i++) {                    // vertical cascade
-            const uint32_t t = v + vs[i];
-            vs[i] = v;
-            v = t;
-        }
-        // S (packed) at row r - NS/2; unpack, E(x) = S(x-1) + S(x+1)
-        const uint32_t sp = __shfl_up_sync(FULL, v, 1), sn = __shfl_down_sync(FULL, v, 1);
-        const int s0 = (int)(v & 0xffffu), s1 = (int)(v >> 16);
-        const int e0 = (int)(sp >> 16) + s1, e1 = s0 + (int)(sn & 0xffffu);
-        const int m = r - R;
-        if (m >= ys) {
-            const int a0 = 2 * (e0_m2 + e0) - 8 * s0_m1, a1 = 2 * (e1_m2 + e1) - 8 * s1_m1;
-            const int o0 = min(255, max(0, a0)), o1 = min(255, max(0, a1));
-            uint8_t *orow = out + (int64_t)m * out_pitch + cx;
-            if (vec) {
-                if (lane_ok) *reinterpret_cast<uint16_t *>(orow) = (uint16_t)(o0 | (o1 << 8));
-            } else {
-                if (st0) orow[0] = (uint8_t)o0;
-                if (st1) orow[1] = (uint8_t)o1;
+            for (int i = 0; i < NS; i++) {                    // vertical cascade
+                const uint32_t t = v + vs[i];
+                vs[i] = v;
+                v = t;
             }
+            // S (packed) at row r - NS/2; unpack, E(x) = S(x-1) + S(x+1)
+            const uint32_t sp = __shfl_up_sync(FULL, v, 1), sn = __shfl_down_sync(FULL, v, 1);
+            const int s0 = (int)(v & 0xffffu), s1 = (int)(v >> 16);
+            const int e0 = (int)(sp >> 16) + s1, e1 = s0 + (int)(sn & 0xffffu);
+            if (r - R >= ys) {
+                const int a0 = 2 * (e0_m2 + e0) - 8 * s0_m1, a1 = 2 * (e1_m2 + e1) - 8 * s1_m1;
+                const int o0 = min(255, max(0, a0)), o1 = min(255, max(0, a1));
+                if (FAST) {
+                    if (lane_ok) *reinterpret_cast<uint16_t *>(po) = (uint16_t)(o0 | (o1 << 8));
+                } else {
+                    if (st0) po[0] = (uint8_t)o0;
+                    if (st1) po[1] = (uint8_t)o1;
+                }
+                po += out_pitch;
+            }
+            e0_m2 = e0_m1; e1_m2 = e1_m1; e0_m1 = e0; e1_m1 = e1;
+            s0_m1 = s0; s1_m1 = s1;
         }
-        e0_m2 = e0_m1; e1_m2 = e1_m1; e0_m1 = e0; e1_m1 = e1;
-        s0_m1 = s0; s1_m1 = s1;
-      }
     }
+}
+
+template <int K, typename T>
+__global__ void __launch_bounds__(LAP_WARPS * 32)
+k_laplacian2(const T *__restrict__ img, int64_t pitch, int w, int h, const uint8_t *__restrict__ lut,
+             const KrDevStats *__restrict__ st, int slot, int invert, uint8_t *__restrict__ out,
+             int64_t out_pitch, int aligned)
+{
+    constexpr int R = K / 2, HL = (R + 1) / 2, VALID = 64 - 4 * HL;
+    float fmn = 0.f, frange = 0.f;
+    if (PixTraits<T>::is_float) {
+        float mn = kr_f32_dec_bits(st->minf_enc[slot], 0), mx = kr_f32_dec_bits(st->maxf_enc[slot], 0);
+        fmn = mn;
+        frange = (mx > mn) ? (float)((double)mx - (double)mn) : 0.f;
+    }
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int xs = (blockIdx.x * LAP_WARPS + wid) * VALID;
+    if (xs >= w) return;
+    const int ys = blockIdx.y * LAP_ROWS, ye = min(ys + LAP_ROWS, h);
+    const bool fast = aligned && (xs - 2 * HL >= 0) && (xs - 2 * HL + 64 <= w) && (ys - R >= 0) &&
+                      (ye + R + 4 <= h);
+    if (fast)
+        lap2_body<K, T, true>(img, pitch, w, h, lut, fmn, frange, invert, out, out_pitch, xs, ys, ye, lane);
+    else
+        lap2_body<K, T, false>(img, pitch, w, h, lut, fmn, frange, invert, out, out_pitch, xs, ys, ye, lane);
 }
 
 template <typename T>
