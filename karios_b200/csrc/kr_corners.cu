@@ -262,6 +262,13 @@ k_eig_candidates(const uint8_t *__restrict__ img, int64_t pitch, const uint8_t *
 constexpr int EC_WARPS = 4, EC_BLOCKS_PER_SM = 3, EC_OUTW = 104, EC_LEFT = 12, EC_CBUF = 256;
 constexpr int EC_RING_F4 = 16 * 2 * 32;          // float4 per warp: 16 rows x (dx, dy) x 32 lanes
 
+// exact int -> float for |i| < 2^22 on the ALU / FMA pipes (the XU pipe that I2F
+// uses is the busiest unit of this kernel)
+__device__ __forceinline__ float i2f_small(int i)
+{
+    return __fsub_rn(__int_as_float(0x4B400000 + i), 12582912.0f);
+}
+
 __device__ __forceinline__ float eig_from_sums(double sxx, double sxy, double syy)
 {
     float a = __fmul_rn((float)sxx, 0.5f), b = (float)sxy, c = __fmul_rn((float)syy, 0.5f);
@@ -321,7 +328,8 @@ __device__ __forceinline__ void eig_stream_body(
     for (int c = 0; c < 3; c++)
 #pragma unroll
         for (int j = 0; j < 4; j++) cs[c][j] = 0.0;
-    float E1[6] = {0, 0, 0, 0, 0, 0}, E2[6] = {0, 0, 0, 0, 0, 0};   // eig rows q-1, q-2: [L, 0..3, R]
+    float E1[6] = {0, 0, 0, 0, 0, 0};                  // eig row q-1: [L, 0..3, R]
+    float H1[4] = {0, 0, 0, 0}, H2[4] = {0, 0, 0, 0};  // 3-wide maxima of eig rows q-1, q-2
     uint32_t my_max = KR_ENC_NEG_INF;
     int ccount = 0;                                                    // warp-uniform
     int nprod = 0;
@@ -345,7 +353,7 @@ __device__ __forceinline__ void eig_stream_body(
         q[5] = (int)(wr & 255u);
         float fq[6];
 #pragma unroll
-        for (int j = 0; j < 6; j++) fq[j] = (float)q[j];
+        for (int j = 0; j < 6; j++) fq[j] = i2f_small(q[j]);
         int R0[4];
         float T0[4];
 #pragma unroll
@@ -368,7 +376,7 @@ __device__ __forceinline__ void eig_stream_body(
             float dxv[4], dyv[4];
 #pragma unroll
             for (int j = 0; j < 4; j++) {
-                dxv[j] = __fmaf_rn(s, (float)(R2[j] + R0[j]), __fmul_rn(s2, (float)R1[j]));
+                dxv[j] = __fmaf_rn(s, i2f_small(R2[j] + R0[j]), __fmul_rn(s2, i2f_small(R1[j])));
                 const float d0 = __fsub_rn(T0[j], T2[j]);
                 dyv[j] = rrefl ? -d0 : d0;                   // exact negation
             }
@@ -419,7 +427,10 @@ __device__ __forceinline__ void eig_stream_body(
                 }
                 E0[0] = __shfl_up_sync(FULL, E0[4], 1);
                 E0[5] = __shfl_down_sync(FULL, E0[1], 1);
-                // ---- 3x3 local maxima of row m = r - 9 ------------------------
+                float H0[4];                                   // 3-wide row maxima of the new row
+#pragma unroll
+                for (int j = 0; j < 4; j++) H0[j] = fmaxf(fmaxf(E0[j], E0[j + 1]), E0[j + 2]);
+                // ---- 3x3 local maxima of row m = r - 9: eig == dilate(eig) ------
                 const int m = r - 9;
                 if (m >= ys && m < ye) {                       // warp-uniform
                     const bool row_ok = emit && m >= 1 && m <= h - 2;
@@ -434,9 +445,9 @@ __device__ __forceinline__ void eig_stream_body(
                             if (DEBUG_EIG) *(float *)((char *)eig_out + (int64_t)m * eig_pitch + (int64_t)x * 4) = v;
                             if (mok) my_max = max(my_max, kr_f32_enc(v));
                         }
-                        bool is_c = row_ok && inimg && mok && v > 0.f && (!BORDER || (x >= 1 && x <= w - 2));
-                        is_c = is_c && v >= E2[j] && v >= E2[j + 1] && v >= E2[j + 2] && v >= E1[j] &&
-                               v >= E1[j + 2] && v >= E0[j] && v >= E0[j + 1] && v >= E0[j + 2];
+                        const float dil = fmaxf(fmaxf(H2[j], H1[j]), H0[j]);
+                        const bool is_c = row_ok && inimg && mok && v > 0.f && v == dil &&
+                                          (!BORDER || (x >= 1 && x <= w - 2));
                         if (is_c) cm |= 1u << j;
                     }
                     if (__any_sync(FULL, cm != 0)) {
@@ -463,7 +474,9 @@ __device__ __forceinline__ void eig_stream_body(
                     }
                 }
 #pragma unroll
-                for (int j = 0; j < 6; j++) { E2[j] = E1[j]; E1[j] = E0[j]; }
+                for (int j = 0; j < 6; j++) E1[j] = E0[j];
+#pragma unroll
+                for (int j = 0; j < 4; j++) { H2[j] = H1[j]; H1[j] = H0[j]; }
             }
         }
 #pragma unroll

@@ -406,12 +406,14 @@ __device__ __forceinline__ void lap2_body(const T *__restrict__ img, int64_t pit
     Vec2<T> raw[PF];
 #pragma unroll
     for (int u = 0; u < PF; u++) raw[u] = load_next();
+    uint32_t vn = norm2(raw[0]);                       // table lookups run one row ahead too
     for (int rb = r_first; rb < r_end; rb += PF) {
 #pragma unroll
         for (int u = 0; u < PF; u++) {
             const int r = rb + u;
             if (r >= r_end) break;
-            uint32_t v = norm2(raw[u]);
+            uint32_t v = vn;
+            vn = norm2(raw[(u + 1) % PF]);
             raw[u] = load_next();
             // horizontal [1,1] cascade on the packed pair, alternating direction
 #pragma unroll
