@@ -65,6 +65,7 @@ typedef struct {
     int32_t invert_mon;         /* laplacian_invert_polarity (klt.py:419) */
     int32_t tail_mode;          /* KR_TAIL_* */
     int32_t compute_zncc;       /* kr_match_tile only: also fill zncc[] */
+    int32_t compute_mi;         /* kr_match_tile only: also fill mutual_info[] / mi[] */
     double quality_level;       /* qualityLevel */
     double min_distance;        /* minDistance */
     double eps;                 /* 0.03 (klt.py:131) */
@@ -94,6 +95,8 @@ typedef struct {
 typedef struct {
     float *x0, *y0, *dx, *dy, *score;   /* float32 columns of the DataFrame */
     double *zncc;                       /* optional (may be NULL) */
+    double *mutual_info;                /* optional: Studholme NMI, api/core.py:894-897 */
+    double *mi;                         /* optional: 2 MI / (Hx + Hy), api/core.py:902-907 */
     int32_t capacity;
 } kr_rows;
 
@@ -173,11 +176,25 @@ KR_API int kr_zncc(kr_ctx *ctx, const void *ref, int64_t ref_pitch, int ref_w, i
                    const float *x0, const float *y0, const float *dx, const float *dy, int n,
                    const int32_t *d_count, double *out, void *stream);
 
+/* MutualInfoService.compute_mutual_info(df, monitored, reference)
+ * (mutual_info_service.py:73-138, _mutual_info :32-63) -> out_studholme, and
+ * ZNCCService.compute_mi(df, monitored, reference) (zncc_service.py:240-287,
+ * _mutual_information :129-151) -> out_nmi, from ONE 32 x 32 joint histogram
+ * (np.histogram2d semantics) of the two 57 x 57 chips per row.  Either output
+ * may be NULL.  NaN where the reference returns NaN (chip outside the raster,
+ * non-finite pixels, zero joint entropy). */
+KR_API int kr_mutual_info(kr_ctx *ctx, const void *ref, int64_t ref_pitch, int ref_w, int ref_h,
+                          const void *mon, int64_t mon_pitch, int mon_w, int mon_h, int dtype,
+                          const float *x0, const float *y0, const float *dx, const float *dy, int n,
+                          const int32_t *d_count, double *out_studholme, double *out_nmi,
+                          void *stream);
+
 /* KLT._match_tile (klt.py:236-349) for one tile window of full-size rasters,
  * without any host synchronisation: auto mask (mask == NULL) or user mask,
  * min/max, uint8 + Laplacian of both windows, klt_tracker, tile offsets,
- * sort by (x0, y0), and optionally ZNCC of rows with score >= zncc_min_score
- * against the FULL rasters (api/core.py:884-891).  mon/ref/mask point at the
+ * sort by (x0, y0), and optionally ZNCC (compute_zncc) and the two mutual-
+ * information scores (compute_mi) of rows with score >= zncc_min_score
+ * against the FULL rasters (api/core.py:884-907).  mon/ref/mask point at the
  * full rasters (img_w x img_h); the tile is [x_off, x_off+tile_w) x
  * [y_off, y_off+tile_h). */
 KR_API int kr_match_tile(kr_ctx *ctx, const void *mon, int64_t mon_pitch, const void *ref,
@@ -191,8 +208,8 @@ KR_API int kr_match_tile(kr_ctx *ctx, const void *mon, int64_t mon_pitch, const 
  * has been synchronised kr_read_stage_ms returns the KR_NUM_STAGES durations
  * (ms) of the last call, in this order: min/max+mask, Laplacian mon, Laplacian
  * ref, corner response, candidate selection, NMS, corner sort, pyramids, LK
- * round trip, row compaction+sort, ZNCC. */
-#define KR_NUM_STAGES 11
+ * round trip, row compaction+sort, ZNCC, mutual information. */
+#define KR_NUM_STAGES 12
 KR_API int kr_set_profiling(kr_ctx *ctx, int on);
 KR_API int kr_read_stage_ms(kr_ctx *ctx, float *ms);
 

@@ -22,19 +22,20 @@ KR_TAIL_NONE, KR_TAIL_AVX512 = 0, 32
 EXPORTS = [
     "kr_version", "kr_last_error", "kr_ctx_create", "kr_ctx_destroy", "kr_read_stats",
     "kr_set_select_all", "kr_minmax_mask", "kr_u8_laplacian", "kr_corner_min_eigen_val",
-    "kr_good_features", "kr_pyr_down", "kr_pyr_lk", "kr_klt_track", "kr_zncc", "kr_match_tile",
+    "kr_good_features", "kr_pyr_down", "kr_pyr_lk", "kr_klt_track", "kr_zncc", "kr_mutual_info",
+    "kr_match_tile",
     "kr_set_profiling", "kr_read_stage_ms",
 ]
-NUM_STAGES = 11
+NUM_STAGES = 12
 STAGE_NAMES = ["minmax_mask", "laplacian_mon", "laplacian_ref", "corner_response", "select",
-               "nms", "corner_sort", "pyramids", "lk_roundtrip", "rows", "zncc"]
+               "nms", "corner_sort", "pyramids", "lk_roundtrip", "rows", "zncc", "mutual_info"]
 
 
 class KltConf(C.Structure):
     _fields_ = [("max_corners", C.c_int32), ("block_size", C.c_int32), ("win_size", C.c_int32),
                 ("max_level", C.c_int32), ("max_count", C.c_int32), ("ksize_mon", C.c_int32),
                 ("ksize_ref", C.c_int32), ("invert_mon", C.c_int32), ("tail_mode", C.c_int32),
-                ("compute_zncc", C.c_int32), ("quality_level", C.c_double),
+                ("compute_zncc", C.c_int32), ("compute_mi", C.c_int32), ("quality_level", C.c_double),
                 ("min_distance", C.c_double), ("eps", C.c_double),
                 ("min_eig_threshold", C.c_double), ("back_threshold", C.c_double),
                 ("zncc_min_score", C.c_double)]
@@ -54,7 +55,8 @@ class Stats(C.Structure):
 
 class Rows(C.Structure):
     _fields_ = [("x0", C.c_void_p), ("y0", C.c_void_p), ("dx", C.c_void_p), ("dy", C.c_void_p),
-                ("score", C.c_void_p), ("zncc", C.c_void_p), ("capacity", C.c_int32)]
+                ("score", C.c_void_p), ("zncc", C.c_void_p), ("mutual_info", C.c_void_p),
+                ("mi", C.c_void_p), ("capacity", C.c_int32)]
 
 
 _lib = None
@@ -98,6 +100,8 @@ def load_library(path: str = LIB_PATH):
                                    i32, Rows, vp]
         L.kr_zncc.argtypes = [vp, vp, i64, i32, i32, vp, i64, i32, i32, i32, vp, vp, vp, vp, i32, vp,
                               vp, vp]
+        L.kr_mutual_info.argtypes = [vp, vp, i64, i32, i32, vp, i64, i32, i32, i32, vp, vp, vp, vp, i32,
+                                     vp, vp, vp, vp]
         L.kr_match_tile.argtypes = [vp, vp, i64, vp, i64, i32, i32, i32, vp, i64, i32, i32, i32, i32,
                                     i32, f64, i32, f64, C.POINTER(KltConf), Rows, vp]
         for name in EXPORTS:
@@ -150,7 +154,7 @@ def _stream() -> int:
 
 
 def make_conf(conf, ksize_mon=None, ksize_ref=None, invert_mon=None, tail_mode=KR_TAIL_AVX512,
-              compute_zncc=False, zncc_min_score=0.4) -> KltConf:
+              compute_zncc=False, zncc_min_score=0.4, compute_mi=False) -> KltConf:
     """KLTConfiguration (karios/core/configuration.py:36-50) + the constants of
     klt.py:128-132,143 -> kr_klt_conf."""
     k = conf.laplacian_kernel_size
@@ -173,6 +177,7 @@ def make_conf(conf, ksize_mon=None, ksize_ref=None, invert_mon=None, tail_mode=K
     c.invert_mon = int(bool(inv) if invert_mon is None and inv != "auto" else bool(invert_mon))
     c.tail_mode = int(tail_mode)
     c.compute_zncc = int(bool(compute_zncc))
+    c.compute_mi = int(bool(compute_mi))
     c.quality_level = float(conf.qualityLevel)
     c.min_distance = float(conf.minDistance)
     c.eps = 0.03
@@ -185,16 +190,20 @@ def make_conf(conf, ksize_mon=None, ksize_ref=None, invert_mon=None, tail_mode=K
 class RowBuffers:
     """Device SoA for the rows of one tile (kr_rows)."""
 
-    def __init__(self, capacity: int, device, with_zncc=True):
+    def __init__(self, capacity: int, device, with_zncc=True, with_mi=False):
         self.capacity = int(capacity)
         self.f32 = torch.empty((5, self.capacity), dtype=torch.float32, device=device)
         self.zncc = torch.empty(self.capacity, dtype=torch.float64, device=device) if with_zncc else None
+        # [0] = mutual_info_score (Studholme), [1] = mi_score (api/core.py:894-907)
+        self.mi = torch.empty((2, self.capacity), dtype=torch.float64, device=device) if with_mi else None
 
     def struct(self) -> Rows:
         r = Rows()
         base, step = self.f32.data_ptr(), self.capacity * 4
         r.x0, r.y0, r.dx, r.dy, r.score = (base + i * step for i in range(5))
         r.zncc = self.zncc.data_ptr() if self.zncc is not None else None
+        r.mutual_info = self.mi[0].data_ptr() if self.mi is not None else None
+        r.mi = self.mi[1].data_ptr() if self.mi is not None else None
         r.capacity = self.capacity
         return r
 
@@ -353,6 +362,19 @@ class Context:
                                     mon.data_ptr(), _pitch(mon), mon.shape[1], mon.shape[0],
                                     dtype_code(ref), x0.data_ptr(), y0.data_ptr(), dx.data_ptr(),
                                     dy.data_ptr(), n, None, out.data_ptr(), _stream()))
+        return out
+
+    def mutual_info(self, ref, mon, x0, y0, dx, dy):
+        """-> [2, n] float64: row 0 = Studholme NMI (MutualInfoService), row 1 =
+        2 MI / (Hx + Hy) (ZNCCService.compute_mi)."""
+        n = x0.shape[0]
+        out = torch.empty((2, n), dtype=torch.float64, device=ref.device)
+        if n:
+            _check(self.lib.kr_mutual_info(self._h, ref.data_ptr(), _pitch(ref), ref.shape[1],
+                                           ref.shape[0], mon.data_ptr(), _pitch(mon), mon.shape[1],
+                                           mon.shape[0], dtype_code(ref), x0.data_ptr(), y0.data_ptr(),
+                                           dx.data_ptr(), dy.data_ptr(), n, None, out[0].data_ptr(),
+                                           out[1].data_ptr(), _stream()))
         return out
 
     def match_tile_async(self, mon, ref, mask, window, kconf: KltConf, rows: RowBuffers,

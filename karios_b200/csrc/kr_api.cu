@@ -367,6 +367,19 @@ KR_API int kr_zncc(kr_ctx *ctx, const void *ref, int64_t ref_pitch, int ref_w, i
                     nullptr, 0.f, n, (const uint32_t *)d_count, out, (cudaStream_t)stream);
 }
 
+KR_API int kr_mutual_info(kr_ctx *ctx, const void *ref, int64_t ref_pitch, int ref_w, int ref_h,
+                          const void *mon, int64_t mon_pitch, int mon_w, int mon_h, int dtype,
+                          const float *x0, const float *y0, const float *dx, const float *dy, int n,
+                          const int32_t *d_count, double *out_studholme, double *out_nmi, void *stream)
+{
+    (void)ctx;
+    if (!ref || !mon || !x0 || !y0 || !dx || !dy || (!out_studholme && !out_nmi))
+        return kr_set_error(KR_ERR_INVALID, "NULL argument");
+    return krl_mutual_info(ref, ref_pitch, ref_w, ref_h, mon, mon_pitch, mon_w, mon_h, dtype, x0, y0,
+                           dx, dy, nullptr, 0.f, n, (const uint32_t *)d_count, out_studholme, out_nmi,
+                           (cudaStream_t)stream);
+}
+
 KR_API int kr_match_tile(kr_ctx *ctx, const void *mon, int64_t mon_pitch, const void *ref,
                          int64_t ref_pitch, int dtype, int img_w, int img_h, const uint8_t *mask,
                          int64_t mask_pitch, int x_off, int y_off, int tile_w, int tile_h,
@@ -410,6 +423,12 @@ KR_API int kr_match_tile(kr_ctx *ctx, const void *mon, int64_t mon_pitch, const 
                         rows.y0, rows.dx, rows.dy, rows.score, (float)conf->zncc_min_score,
                         rows.capacity, &ctx->d_stats->n_kept, rows.zncc, s));
     KR_MARK(ctx, 11, s);
+    if (conf->compute_mi && (rows.mutual_info || rows.mi))
+        KR_TRY(krl_mutual_info(ref, ref_pitch, img_w, img_h, mon, mon_pitch, img_w, img_h, dtype,
+                               rows.x0, rows.y0, rows.dx, rows.dy, rows.score,
+                               (float)conf->zncc_min_score, rows.capacity, &ctx->d_stats->n_kept,
+                               rows.mutual_info, rows.mi, s));
+    KR_MARK(ctx, 12, s);
     return KR_OK;
 }
 

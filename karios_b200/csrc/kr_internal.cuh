@@ -5,6 +5,7 @@
 //   kr_sort.cu     chunk bitonic sort + rank merge (u64 keys)
 //   kr_lk.cu       K5 pyrDown, K6 pyramidal LK (forward + backward + back-check)
 //   kr_zncc.cu     K7 ZNCC
+//   kr_mi.cu       K8 mutual-information scores (32 x 32 joint histogram per match)
 //   kr_api.cu      context, error handling, C ABI (include/karios_b200.h)
 #pragma once
 #include <cuda_runtime.h>
@@ -155,3 +156,7 @@ int krl_zncc(const void *ref, int64_t rp, int rw, int rh, const void *mon, int64
              int dtype, const float *x0, const float *y0, const float *dx, const float *dy,
              const float *score, float min_score, int n, const uint32_t *d_count, double *out,
              cudaStream_t s);
+int krl_mutual_info(const void *ref, int64_t rp, int rw, int rh, const void *mon, int64_t mp, int mw,
+                    int mh, int dtype, const float *x0, const float *y0, const float *dx,
+                    const float *dy, const float *score, float min_score, int n,
+                    const uint32_t *d_count, double *out_studholme, double *out_nmi, cudaStream_t s);

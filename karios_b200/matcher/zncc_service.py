@@ -47,6 +47,18 @@ def _raster_tensor(img, dev) -> torch.Tensor:
     return N.to_device(img.array, dev)
 
 
+def _score_inputs(df, monitored, reference):
+    """(ref tensor, mon tensor, [x0, y0, dx, dy] float32 device columns)."""
+    dev = torch.device("cuda", torch.cuda.current_device())
+    mon = _raster_tensor(monitored, dev)
+    ref = _raster_tensor(reference, dev)
+    if mon.dtype != ref.dtype:
+        raise N.KariosB200Error("monitored and reference rasters must share a dtype")
+    cols = [torch.from_numpy(np.ascontiguousarray(df[c].to_numpy(np.float32))).to(dev)
+            for c in ("x0", "y0", "dx", "dy")]
+    return ref, mon, cols
+
+
 class ZNCCService:
     """Zero-mean normalised cross-correlation between chips of two rasters."""
 
@@ -61,17 +73,27 @@ class ZNCCService:
         if len(df) == 0:
             score = Series(np.empty(0, np.float64), index=df.index, dtype=np.float64)
         else:
-            dev = torch.device("cuda", torch.cuda.current_device())
-            mon = _raster_tensor(monitored, dev)
-            ref = _raster_tensor(reference, dev)
-            if mon.dtype != ref.dtype:
-                raise N.KariosB200Error("monitored and reference rasters must share a dtype")
-            cols = [torch.from_numpy(np.ascontiguousarray(df[c].to_numpy(np.float32))).to(dev)
-                    for c in ("x0", "y0", "dx", "dy")]
+            ref, mon, cols = _score_inputs(df, monitored, reference)
             ctx = get_context(64, 64, 1024)
             z = ctx.zncc(ref, mon, *cols)
             score = Series(z.cpu().numpy(), index=df.index, dtype=np.float64)
         monitored.clear_cache()
         reference.clear_cache()
         logger.info("ZNCC computation finish")
+        return score
+
+    def compute_mi(self, df: DataFrame, monitored, reference) -> Series:
+        """NMI = 2 MI / (H(X) + H(Y)) of the 57x57 chips of each key point
+        (zncc_service.py:240-287, _mutual_information :129-151): one launch of
+        kr_mutual_info instead of the per-row np.histogram2d loop."""
+        logger.info("Compute NMI for %s points", len(df))
+        if len(df) == 0:
+            score = Series(np.empty(0, np.float64), index=df.index, dtype=np.float64)
+        else:
+            ref, mon, cols = _score_inputs(df, monitored, reference)
+            mi = get_context(64, 64, 1024).mutual_info(ref, mon, *cols)
+            score = Series(mi[1].cpu().numpy(), index=df.index, dtype=np.float64)
+        monitored.clear_cache()
+        reference.clear_cache()
+        logger.info("NMI computation finish")
         return score

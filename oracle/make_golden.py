@@ -154,6 +154,76 @@ def zncc_known_answers():
     print("zncc_known", {k: float(v) for k, v in out.items() if k.startswith("z_")})
 
 
+def mi_golden():
+    """Mutual-information scores through the UNMODIFIED reference:
+    _mutual_info (mutual_info_service.py:32-63), _mutual_information
+    (zncc_service.py:129-151) on the patch families of the reference's own
+    known-answer tests (tests/test_mutual_info_service.py: identical, correlated,
+    independent, one uniform, both uniform) in the raster dtypes the CUDA path
+    takes, and MutualInfoService.compute_mutual_info / ZNCCService.compute_mi on
+    the rows of a synthetic pair, border rows included."""
+    _, zs, _ = refimport.load()
+    mis = refimport.load_mutual_info()
+    out = {}
+    rng = np.random.default_rng(42)
+    base = rng.random((57, 57))
+    fam = {
+        "ident": (np.arange(57 * 57, dtype=np.float64).reshape(57, 57),) * 2,
+        "corr": (base, base + rng.random((57, 57)) * 0.1),
+        "indep": (rng.random((57, 57)), rng.random((57, 57))),
+        "unif1": (np.ones((57, 57)), rng.random((57, 57))),
+        "unif2": (np.ones((57, 57)), np.ones((57, 57))),
+    }
+    for name, (a, b) in fam.items():
+        for dt, scale in (("f32", 1.0), ("u16", 6000.0), ("u8", 255.0)):
+            if dt == "f32":
+                pa, pb = a.astype(np.float32), b.astype(np.float32)
+            else:
+                t = np.uint16 if dt == "u16" else np.uint8
+                sa = scale / max(1.0, a.max())
+                sb = scale / max(1.0, b.max())
+                pa, pb = (a * sa).astype(t), (b * sb).astype(t)
+            out[f"{name}_{dt}_a"], out[f"{name}_{dt}_b"] = pa, pb
+            out[f"{name}_{dt}_studholme"] = mis._mutual_info(pa, pb)
+            out[f"{name}_{dt}_nmi"] = zs._mutual_information(pa, pb)
+    # service level, uint16 rasters
+    ref_t, mon_t = synth.make_pair(300, 420, seed=11, shift=(0.30, -0.20))
+    ref, mon = _np16(ref_t), _np16(mon_t)
+    ref[100:170, 200:280] = 1500            # a flat area: one-bin chips -> NaN / 1.0 / 0.0
+    mon[100:170, 200:280] = 1500
+    mon[20:60, 300:330] = 0
+    n = 160
+    x0 = rng.uniform(0, 420, n).astype(np.float32)
+    y0 = rng.uniform(0, 300, n).astype(np.float32)
+    x0[:6] = [28.0, 27.9, 391.0, 392.0, 240.0, 238.5]
+    y0[:6] = [28.0, 60.0, 271.0, 100.0, 135.0, 133.5]
+    dx = rng.uniform(-1.5, 1.5, n).astype(np.float32)
+    dy = rng.uniform(-1.5, 1.5, n).astype(np.float32)
+    dx[4:6] = 0.25
+    dy[4:6] = -0.25
+    df = pd.DataFrame({"x0": x0, "y0": y0, "dx": dx, "dy": dy})
+    mon_img, ref_img = refimport.ArrayImage(mon), refimport.ArrayImage(ref)
+    out.update(svc_ref=ref, svc_mon=mon, svc_x0=x0, svc_y0=y0, svc_dx=dx, svc_dy=dy)
+    out["svc_studholme"] = mis.MutualInfoService().compute_mutual_info(df, mon_img, ref_img).to_numpy(np.float64)
+    out["svc_nmi"] = zs.ZNCCService().compute_mi(df, mon_img, ref_img).to_numpy(np.float64)
+    # float32 rasters with a NaN and an Inf pixel (np.histogram2d raises -> NaN)
+    reff, monf = ref.astype(np.float32) / 7, mon.astype(np.float32) / 7
+    reff[50, 50] = np.nan
+    monf[250, 100] = np.inf
+    out.update(svc_ref_f32=reff, svc_mon_f32=monf)
+    import logging
+    logging.disable(logging.CRITICAL)
+    out["svc_studholme_f32"] = mis.MutualInfoService().compute_mutual_info(
+        df, refimport.ArrayImage(monf), refimport.ArrayImage(reff)).to_numpy(np.float64)
+    out["svc_nmi_f32"] = zs.ZNCCService().compute_mi(
+        df, refimport.ArrayImage(monf), refimport.ArrayImage(reff)).to_numpy(np.float64)
+    logging.disable(logging.NOTSET)
+    np.savez_compressed(os.path.join(OUT, "mi_known.npz"), **out)
+    print("mi_known", {k: float(v) for k, v in out.items() if k.endswith("u16_studholme") or k.endswith("u16_nmi")},
+          "svc NaN", int(np.isnan(out["svc_studholme"]).sum()), int(np.isnan(out["svc_nmi"]).sum()),
+          int(np.isnan(out["svc_studholme_f32"]).sum()))
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     cv2.setNumThreads(1)
@@ -169,3 +239,4 @@ if __name__ == "__main__":
               matching_winsize=15, outliers_filtering=True, qualityLevel=0.02, minDistance=5,
               blocksize=7, maxCorners=2000), negate_mon=True)
     zncc_known_answers()
+    mi_golden()

@@ -377,3 +377,85 @@ def _zncc_one(x0f, y0f, dxf, dyf, monitored, reference):
         return zncc2(cr, cm, 28, 28, 28, 28, 21)
     except Exception:  # noqa: BLE001 - mirrors zncc_service.py:232-238
         return np.nan
+
+
+# --------------------------------------------------------------------------- f1
+def mutual_info_studholme(patch1, patch2, bins=32):
+    """_mutual_info (mutual_info_service.py:32-63): (H(X) + H(Y)) / H(X, Y),
+    natural logarithm, np.histogram2d with per-patch min/max edges."""
+    hist_2d, _, _ = np.histogram2d(patch1.ravel(), patch2.ravel(), bins=bins)
+    n = hist_2d.sum()
+    if n == 0:
+        return np.nan
+    pxy = hist_2d / n
+    px, py = pxy.sum(axis=1), pxy.sum(axis=0)
+    hx = -np.sum(px[px > 0] * np.log(px[px > 0]))
+    hy = -np.sum(py[py > 0] * np.log(py[py > 0]))
+    hxy = -np.sum(pxy[pxy > 0] * np.log(pxy[pxy > 0]))
+    if hxy == 0:
+        return np.nan
+    return float((hx + hy) / hxy)
+
+
+def mutual_info_nmi(patch1, patch2, bins=32):
+    """_mutual_information (zncc_service.py:129-151): 2 MI / (H(X) + H(Y)), log2."""
+    p1 = patch1.ravel().astype(np.float64)
+    p2 = patch2.ravel().astype(np.float64)
+    joint_hist, _, _ = np.histogram2d(p1, p2, bins=bins)
+    joint_prob = joint_hist / joint_hist.sum()
+
+    def entropy(p):
+        p = p[p > 0]
+        return float(-np.sum(p * np.log2(p)))
+
+    h_x, h_y = entropy(joint_prob.sum(axis=1)), entropy(joint_prob.sum(axis=0))
+    h_xy = entropy(joint_prob.ravel())
+    denom = h_x + h_y
+    if denom == 0:
+        return np.nan
+    return float(2.0 * (h_x + h_y - h_xy) / denom)
+
+
+def joint_histogram_int(patch1, patch2, bins=32):
+    """The same joint histogram for INTEGER patches without floating point: the
+    linspace edges are the exact rationals min + k (max - min) / bins, so the bin
+    is ((v - min) * bins) // (max - min), capped at bins - 1; a constant patch
+    falls into bin bins // 2 (edges min - 0.5 ... max + 0.5).  This is the form
+    the CUDA kernel uses; tests check it against np.histogram2d."""
+    def bin_of(p):
+        v = p.ravel().astype(np.int64)
+        mn, mx = int(v.min()), int(v.max())
+        if mx == mn:
+            return np.full(v.shape, bins // 2, np.int64)
+        return np.minimum(bins - 1, ((v - mn) * bins) // (mx - mn))
+    ka, kb = bin_of(patch1), bin_of(patch2)
+    return np.bincount(ka * bins + kb, minlength=bins * bins).reshape(bins, bins)
+
+
+def mutual_info(x0, y0, dx, dy, monitored: np.ndarray, reference: np.ndarray):
+    """MutualInfoService.compute_mutual_info (mutual_info_service.py:73-138) and
+    ZNCCService.compute_mi (zncc_service.py:240-287) over float32 columns ->
+    (studholme [n], nmi [n]) float64; NaN where the reference returns NaN."""
+    n = len(x0)
+    st, mi = np.full(n, np.nan), np.full(n, np.nan)
+    m = 28
+    for i in range(n):
+        x0f, y0f = np.float32(x0[i]), np.float32(y0[i])
+        ax, ay = int(x0f), int(y0f)
+        bx, by = round(x0f + np.float32(dx[i])), round(y0f + np.float32(dy[i]))
+        if ax - m < 0 or ay - m < 0 or bx - m < 0 or by - m < 0:
+            continue
+        if (ax >= reference.shape[1] - m or ay >= reference.shape[0] - m
+                or bx >= monitored.shape[1] - m or by >= monitored.shape[0] - m):
+            continue
+        cr = reference[ay - m:ay + m + 1, ax - m:ax + m + 1]
+        cm = monitored[by - m:by + m + 1, bx - m:bx + m + 1]
+        try:
+            st[i] = mutual_info_studholme(cr, cm)
+        except Exception:  # noqa: BLE001 - mutual_info_service.py:122-126
+            pass
+        try:
+            mi[i] = mutual_info_nmi(cr, cm)
+        except Exception:  # noqa: BLE001 - zncc_service.py:283-287
+            pass
+    return st, mi

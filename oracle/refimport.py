@@ -46,6 +46,12 @@ def load():
     return klt, zs, cfg
 
 
+def load_mutual_info():
+    """-> the unmodified karios/matcher/mutual_info_service.py module."""
+    load()
+    return importlib.import_module("karios.matcher.mutual_info_service")
+
+
 class ArrayImage:
     """Duck-typed stand-in for GdalRasterImage (karios/core/image.py:255) over an
     in-memory array: .read/.array/.x_size/.y_size/.no_data_value/.clear_cache."""

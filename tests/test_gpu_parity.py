@@ -293,6 +293,87 @@ def test_zncc_known_answers(golden, N, ctx):
     assert abs(one(af, bf) - O.zncc2(af.astype(np.float64), bf.astype(np.float64), 28, 28, 28, 28, 21)) < 1e-9
 
 
+MI_TOL = 1e-9        # float64 entropies from integer counts vs NumPy's sums of p log p
+
+
+def _mi_close(got, want):
+    got, want = np.asarray(got, np.float64), np.asarray(want, np.float64)
+    assert np.array_equal(np.isnan(got), np.isnan(want)), (np.isnan(got).sum(), np.isnan(want).sum())
+    assert (np.nan_to_num(np.abs(got - want)) <= MI_TOL).all(), np.nanmax(np.abs(got - want))
+
+
+def test_mutual_info_known_answers(golden, N, ctx):
+    """Patch families of the reference's known-answer tests
+    (/root/reference/tests/test_mutual_info_service.py:15-62) through kr_mutual_info,
+    against the values of the unmodified _mutual_info / _mutual_information."""
+    g = golden("mi_known")
+    f = lambda v: torch.tensor([v], dtype=torch.float32, device="cuda")  # noqa: E731
+    for fam in ("ident", "corr", "indep", "unif1", "unif2"):
+        for dt in ("f32", "u16", "u8"):
+            a, b = g[f"{fam}_{dt}_a"], g[f"{fam}_{dt}_b"]
+            out = ctx.mutual_info(dev(a), dev(b), f(28.0), f(28.0), f(0.0), f(0.0)).cpu().numpy()
+            _mi_close(out[0], [float(g[f"{fam}_{dt}_studholme"])])
+            _mi_close(out[1], [float(g[f"{fam}_{dt}_nmi"])])
+    out = ctx.mutual_info(dev(g["ident_u16_a"]), dev(g["ident_u16_a"]), f(28.0), f(28.0), f(0.0), f(0.0))
+    assert abs(float(out[0, 0]) - 2.0) < 1e-10 and abs(float(out[1, 0]) - 1.0) < 1e-10
+    # int16 rasters with negative values
+    rng = np.random.default_rng(8)
+    a = rng.integers(-3000, 3000, (57, 57)).astype(np.int16)
+    b = (a // 3 + rng.integers(-200, 200, (57, 57))).astype(np.int16)
+    out = ctx.mutual_info(dev(a), dev(b), f(28.0), f(28.0), f(0.0), f(0.0)).cpu().numpy()
+    _mi_close(out[0], [O.mutual_info_studholme(a, b)])
+    _mi_close(out[1], [O.mutual_info_nmi(a, b)])
+
+
+def test_mutual_info_services(golden):
+    """MutualInfoService.compute_mutual_info / ZNCCService.compute_mi drop-ins on the
+    golden rows (border rows, flat areas, NaN / Inf pixels in float rasters)."""
+    import pandas as pd
+    from karios_b200.core.image import ArrayRaster
+    from karios_b200.matcher.mutual_info_service import MutualInfoService
+    from karios_b200.matcher.zncc_service import ZNCCService
+    g = golden("mi_known")
+    df = pd.DataFrame({k: g["svc_" + k] for k in ("x0", "y0", "dx", "dy")}, index=np.arange(160)[::-1])
+    for suffix in ("", "_f32"):
+        mon, ref = ArrayRaster(g["svc_mon" + suffix]), ArrayRaster(g["svc_ref" + suffix])
+        st = MutualInfoService().compute_mutual_info(df, mon, ref)
+        mi = ZNCCService().compute_mi(df, mon, ref)
+        assert st.index.equals(df.index) and mi.index.equals(df.index)
+        _mi_close(st.to_numpy(), g["svc_studholme" + suffix])
+        _mi_close(mi.to_numpy(), g["svc_nmi" + suffix])
+    empty = MutualInfoService().compute_mutual_info(df.iloc[:0], mon, ref)
+    assert len(empty) == 0
+
+
+def test_mutual_info_fused_in_match_tile(N):
+    """kr_match_tile with compute_mi: the scores of the fused launch sequence equal
+    the oracle's on the rows it produced (NaN below the confidence threshold)."""
+    from karios_b200 import synth
+    from karios_b200.core.configuration import KLTConfiguration
+    ref_t, mon_t = synth.make_pair(400, 520, seed=31)
+    to_np = lambda t: t.view(torch.int16).numpy().view(np.uint16)  # noqa: E731
+    ref, mon = to_np(ref_t), to_np(mon_t)
+    conf = KLTConfiguration(maxCorners=600)
+    c = N.Context(520, 400, 600)
+    try:
+        rows = N.RowBuffers(600, torch.device("cuda"), with_zncc=True, with_mi=True)
+        kconf = N.make_conf(conf, compute_zncc=True, compute_mi=True, zncc_min_score=0.4)
+        st = c.match_tile(dev(mon), dev(ref), None, (0, 0, 520, 400), kconf, rows)
+        n = int(st.n_kept)
+        f = rows.f32[:, :n].cpu().numpy()
+        got = rows.mi[:, :n].cpu().numpy()
+    finally:
+        c.close()
+    assert n > 100
+    want_st, want_mi = O.mutual_info(f[0], f[1], f[2], f[3], mon, ref)
+    low = f[4] < np.float32(0.4)
+    want_st[low] = np.nan
+    want_mi[low] = np.nan
+    _mi_close(got[0], want_st)
+    _mi_close(got[1], want_mi)
+    assert (~np.isnan(got[0])).sum() > 50
+
+
 def test_sort_and_unlimited_corners(N):
     """maxCorners = 0 exercises the multi-chunk sort and the full NMS."""
     from karios_b200 import synth

@@ -169,3 +169,61 @@ def test_cv2_path_matches_golden(golden, name):
     z = np.concatenate([t["zncc"] for t in tiles])
     assert np.array_equal(np.isnan(z), np.isnan(g["zncc"]))
     assert np.nanmax(np.abs(z - g["zncc"])) < 1e-12
+
+
+# ------------------------------------------------------------------ f1: mutual information
+MI_FAMILIES = ["ident", "corr", "indep", "unif1", "unif2"]
+
+
+def _same(a, b, tol=1e-12):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return np.array_equal(np.isnan(a), np.isnan(b)) and (np.nan_to_num(np.abs(a - b)) <= tol).all()
+
+
+@pytest.mark.parametrize("fam", MI_FAMILIES)
+@pytest.mark.parametrize("dt", ["f32", "u16", "u8"])
+def test_mutual_info_patches_match_reference(golden, fam, dt):
+    """oracle restatement vs the unmodified _mutual_info / _mutual_information on the
+    patch families of /root/reference/tests/test_mutual_info_service.py:15-62."""
+    g = golden("mi_known")
+    a, b = g[f"{fam}_{dt}_a"], g[f"{fam}_{dt}_b"]
+    assert _same(O.mutual_info_studholme(a, b), g[f"{fam}_{dt}_studholme"])
+    assert _same(O.mutual_info_nmi(a, b), g[f"{fam}_{dt}_nmi"])
+
+
+def test_mutual_info_known_answers(golden):
+    """The reference's own assertions (test_mutual_info_service.py:15-62)."""
+    g = golden("mi_known")
+    assert abs(float(g["ident_u16_studholme"]) - 2.0) < 1e-10
+    assert 1.0 <= float(g["corr_f32_studholme"]) <= 2.0
+    assert 1.0 <= float(g["indep_f32_studholme"]) < 1.2
+    assert abs(float(g["unif1_f32_studholme"]) - 1.0) < 1e-10
+    assert np.isnan(g["unif2_f32_studholme"]) and np.isnan(g["unif2_u16_nmi"])
+
+
+def test_mutual_info_service_rows_match_reference(golden):
+    g = golden("mi_known")
+    cols = [g[k] for k in ("svc_x0", "svc_y0", "svc_dx", "svc_dy")]
+    st, mi = O.mutual_info(*cols, g["svc_mon"], g["svc_ref"])
+    assert _same(st, g["svc_studholme"]) and _same(mi, g["svc_nmi"])
+    assert 0 < np.isnan(st).sum() < len(st)
+    st, mi = O.mutual_info(*cols, g["svc_mon_f32"], g["svc_ref_f32"])
+    assert _same(st, g["svc_studholme_f32"]) and _same(mi, g["svc_nmi_f32"])
+    assert np.isnan(st).sum() > np.isnan(g["svc_studholme"]).sum()     # the NaN / Inf pixels
+
+
+def test_integer_joint_histogram_equals_numpy():
+    """The float-free binning the CUDA kernel uses is np.histogram2d's."""
+    rng = np.random.default_rng(5)
+    for trial in range(60):
+        hi = int(rng.choice([1, 2, 31, 32, 33, 255, 1000, 4095, 65535]))
+        dt = np.uint16 if hi > 255 else np.uint8
+        a = rng.integers(0, hi + 1, (57, 57)).astype(dt)
+        b = rng.integers(0, hi + 1, (57, 57)).astype(dt)
+        if trial % 7 == 0:
+            b[:] = b[0, 0]
+        want = np.histogram2d(a.ravel(), b.ravel(), bins=32)[0]
+        assert np.array_equal(O.joint_histogram_int(a, b), want), (trial, hi)
+    a = rng.integers(-3000, 3000, (57, 57)).astype(np.int16)
+    b = rng.integers(-32768, 32767, (57, 57)).astype(np.int16)
+    assert np.array_equal(O.joint_histogram_int(a, b), np.histogram2d(a.ravel(), b.ravel(), bins=32)[0])
