@@ -15,9 +15,13 @@
 //
 // Integer rasters: edges are the exact rationals min + k (max - min) / 32, so the
 // bin is the integer quotient ((v - min) * 32) / (max - min), capped at 31.
-// Float rasters: edges evaluated in float64 exactly like linspace (k * step, then
-// + start, two roundings; last edge = max) and the quotient guess is corrected
-// against them.  Entropies come from the integer counts: H = ln n - sum(c ln c)/n.
+// Float rasters: edges evaluated exactly like linspace (k * step, then + start,
+// two roundings; last edge = max) and the quotient guess is corrected against
+// them -- in float32 for MutualInfoService, which hands float32 chips to
+// np.histogram2d (float32 min/max -> float32 linspace), and in float64 for
+// compute_mi, which casts the chips to float64 first (zncc_service.py:134-135);
+// so float rasters build two histograms.  Entropies come from the integer
+// counts: H = ln n - sum(c ln c) / n.
 //
 // One warp per match: pass 1 min/max of both chips, pass 2 (the chips now sit in
 // L1/L2) shared-memory joint histogram, pass 3 one histogram row per lane.
@@ -80,9 +84,50 @@ __device__ __forceinline__ int float_bin(double v, double start, double stop, do
     return k;
 }
 
+// the same with float32 edges (np.linspace on float32 scalars stays float32)
+__device__ __forceinline__ float edge_at32(int k, float start, float stop, float step)
+{
+    return k >= M_BINS ? stop : __fadd_rn(__fmul_rn((float)k, step), start);
+}
+__device__ __forceinline__ int float_bin32(float v, float start, float stop, float step)
+{
+    if (!(step > 0.f)) return M_BINS / 2;
+    int k = (int)__fdiv_rn(__fsub_rn(v, start), step);
+    k = max(0, min(M_BINS - 1, k));
+    while (k > 0 && v < edge_at32(k, start, stop, step)) k--;
+    while (k < M_BINS - 1 && v >= edge_at32(k + 1, start, stop, step)) k++;
+    return k;
+}
+
 __device__ __forceinline__ double clogc(uint32_t c)
 {
     return c > 1u ? (double)c * log((double)c) : 0.0;
+}
+
+// One joint histogram (a warp's shared-memory copy) -> both scores; lane = one row
+// of the histogram (rotated columns: no bank conflicts).  Leaves NaN when all
+// pixels share one joint bin: H(X,Y) == 0, and then also H(X) + H(Y) == 0.
+__device__ __forceinline__ void scores_from_hist(const uint32_t *hist, int lane, double &r_st, double &r_mi)
+{
+    uint32_t rowsum = 0, colsum = 0, cmax = 0;
+    double sxy = 0.0;
+#pragma unroll 4
+    for (int j = 0; j < M_BINS; j++) {
+        const uint32_t cj = hist[lane * M_BINS + ((j + lane) & (M_BINS - 1))];
+        rowsum += cj;
+        cmax = max(cmax, cj);
+        if (cj > 1u) sxy += (double)cj * log((double)cj);
+        colsum += hist[j * M_BINS + lane];
+    }
+    const double sx = wsumd(clogc(rowsum)), sy = wsumd(clogc(colsum));
+    sxy = wsumd(sxy);
+    cmax = (uint32_t)wmax((int)cmax);
+    if (cmax < (uint32_t)M_N) {
+        const double ln_n = log((double)M_N), inv_n = 1.0 / (double)M_N;
+        const double hx = ln_n - sx * inv_n, hy = ln_n - sy * inv_n, hxy = ln_n - sxy * inv_n;
+        r_st = (hx + hy) / hxy;
+        r_mi = 2.0 * (hx + hy - hxy) / (hx + hy);
+    }
 }
 
 template <typename T>
@@ -152,6 +197,25 @@ k_mutual_info(const T *__restrict__ ref, int64_t rp, int rw, int rh, const T *__
                 ok = __all_sync(0xffffffffu, fin);              // np.histogram2d raises -> NaN
                 mna = wminf(mna); mxa = wmaxf(mxa); mnb = wminf(mnb); mxb = wmaxf(mxb);
                 if (ok) {
+                    // float32 edges -> Studholme score
+                    const float st32a = __fdiv_rn(__fsub_rn(mxa, mna), (float)M_BINS);
+                    const float st32b = __fdiv_rn(__fsub_rn(mxb, mnb), (float)M_BINS);
+                    r = 0; c = lane;
+                    for (int p = lane; p < M_N; p += 32) {
+                        const float a = (float)row_ptr(pa, rp, r)[c], b = (float)row_ptr(pb, mp, r)[c];
+                        const int ka = float_bin32(a, mna, mxa, st32a), kb = float_bin32(b, mnb, mxb, st32b);
+                        atomicAdd(&hist[ka * M_BINS + kb], 1u);
+                        c += 32;
+                        if (c >= M_SIDE) { c -= M_SIDE; r++; }
+                    }
+                    __syncwarp();
+                    double unused = qnan;
+                    scores_from_hist(hist, lane, r_st, unused);
+                    __syncwarp();
+#pragma unroll
+                    for (int j = 0; j < M_BINS; j++) hist[j * M_BINS + lane] = 0u;
+                    __syncwarp();
+                    // float64 edges -> compute_mi score (histogram consumed below)
                     const double sa = (double)mna, ea = (double)mxa, sb = (double)mnb, eb = (double)mxb;
                     const double stepa = (ea - sa) / M_BINS, stepb = (eb - sb) / M_BINS;
                     r = 0; c = lane;
@@ -166,25 +230,11 @@ k_mutual_info(const T *__restrict__ ref, int64_t rp, int rw, int rh, const T *__
             }
             __syncwarp();
             if (ok) {
-                // lane = one row of the joint histogram (rotated columns: no bank conflicts)
-                uint32_t rowsum = 0, colsum = 0, cmax = 0;
-                double sxy = 0.0;
-#pragma unroll 4
-                for (int j = 0; j < M_BINS; j++) {
-                    const uint32_t cj = hist[lane * M_BINS + ((j + lane) & (M_BINS - 1))];
-                    rowsum += cj;
-                    cmax = max(cmax, cj);
-                    if (cj > 1u) sxy += (double)cj * log((double)cj);
-                    colsum += hist[j * M_BINS + lane];
-                }
-                const double sx = wsumd(clogc(rowsum)), sy = wsumd(clogc(colsum));
-                sxy = wsumd(sxy);
-                cmax = (uint32_t)wmax((int)cmax);
-                if (cmax < (uint32_t)M_N) {                     // H(X,Y) > 0 (and H(X) + H(Y) > 0)
-                    const double ln_n = log((double)M_N), inv_n = 1.0 / (double)M_N;
-                    const double hx = ln_n - sx * inv_n, hy = ln_n - sy * inv_n, hxy = ln_n - sxy * inv_n;
-                    r_st = (hx + hy) / hxy;
-                    r_mi = 2.0 * (hx + hy - hxy) / (hx + hy);
+                if (MTraits<T>::is_float) {
+                    double unused = qnan;
+                    scores_from_hist(hist, lane, unused, r_mi);
+                } else {
+                    scores_from_hist(hist, lane, r_st, r_mi);
                 }
             }
             __syncwarp();

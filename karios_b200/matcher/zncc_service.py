@@ -54,7 +54,7 @@ def _score_inputs(df, monitored, reference):
     ref = _raster_tensor(reference, dev)
     if mon.dtype != ref.dtype:
         raise N.KariosB200Error("monitored and reference rasters must share a dtype")
-    cols = [torch.from_numpy(np.ascontiguousarray(df[c].to_numpy(np.float32))).to(dev)
+    cols = [torch.from_numpy(np.array(df[c].to_numpy(np.float32), copy=True)).to(dev)
             for c in ("x0", "y0", "dx", "dy")]
     return ref, mon, cols
 
