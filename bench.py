@@ -37,6 +37,8 @@ def parse():
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
     ap.add_argument("--size", type=int, default=S2, help="scene side (default: the S2 10 m band)")
     ap.add_argument("--scenes", type=int, default=2, help="distinct synthetic scenes per rank")
+    ap.add_argument("--depth", type=int, default=3,
+                    help="scene pairs in flight per GPU (independent contexts + streams)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
@@ -183,6 +185,7 @@ def stage_bytes(P, C, n_corners, n_z):
         "lk_roundtrip": n_corners * 2 * 2 * win_bytes,
         "rows": n_corners * 20,
         "zncc": n_z * 2 * 43 * 43 * 2,
+        "mutual_info": 0,          # not part of the headline path (timed under next_rows)
     }
 
 
@@ -217,17 +220,12 @@ def cuda_arm(args):
         ref, mon = synth.make_pair(size, size, seed=1234 + rank + i * world, device=dev)
         scenes.append((mon, ref))
     torch.cuda.synchronize()
-    sm = SceneMatcher(size, size, conf, 0.4, device=dev)
+    sm = SceneMatcher(size, size, conf, 0.4, device=dev, depth=args.depth)
 
     from karios_b200 import sharding
 
-    def step(i):
-        mon, ref = scenes[i % len(scenes)]
-        return sm.match_device(mon, ref, None, collect=True)
-
     sampler = ClockSampler(local)          # NVML is initialised before the timed region
-    for i in range(args.warmup):
-        step(i)
+    sm.match_many([scenes[i % len(scenes)] for i in range(args.warmup)])
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
@@ -235,19 +233,16 @@ def cuda_arm(args):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
     e0.record()
-    matches = 0
-    tables = []
-    for i in range(args.steps):
-        tiles, n = step(i)
-        matches += n
-        tables.append(tiles)
+    # K steps = K scene pairs, `depth` of them in flight (each on its own context
+    # and stream); every pair's rows are collected
+    tables, matches = sm.match_many([scenes[i % len(scenes)] for i in range(args.steps)])
     if world > 1:
         # the one exchange step of the path: every rank ends with the match tables of
         # all world*steps scene pairs (all_reduce of counts + NCCL all_gather of rows)
         # and the global dx/dy moments
         n_units = world * args.steps
         ids = [rank + i * world for i in range(args.steps)]
-        packed = [torch.cat([sharding.pack_rows(f, z) for f, z in t]) if t else
+        packed = [torch.cat([sharding.pack_rows(t_[0], t_[1]) for t_ in t]) if t else
                   torch.zeros((0, 6), dtype=torch.float64, device=dev) for t in tables]
         merged = sharding.gather_matches(ids, packed, n_units)
         sharding.gather_moments(torch.cat(packed))
@@ -292,6 +287,33 @@ def cuda_arm(args):
     total_alg = sum(sb.values())
     total_ms = sum(v for v in acc.values() if v > 0)
 
+    # ---- SURVEY 8(f) rows built so far, timed on the rows of the last pair -----
+    next_rows = {}
+    try:
+        mon, ref = scenes[0]
+        cols = [sm.rows.f32[i, : st.n_kept].contiguous() for i in range(4)]
+        for _ in range(2):
+            sm.ctx.mutual_info(ref, mon, *cols)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        a.record()
+        reps_mi = 5
+        for _ in range(reps_mi):
+            mi_out = sm.ctx.mutual_info(ref, mon, *cols)
+        b.record()
+        torch.cuda.synchronize()
+        mi_ms = a.elapsed_time(b) / reps_mi
+        n_mi = int((~torch.isnan(mi_out[0])).sum().item())
+        mi_bytes = n_mi * 2 * 57 * 57 * 2
+        next_rows["mutual_info"] = {
+            "what": "MutualInfoService.compute_mutual_info + ZNCCService.compute_mi (one launch, both scores)",
+            "rows": int(st.n_kept), "rows_scored": n_mi, "ms": round(mi_ms, 4),
+            "rows_per_sec": round(int(st.n_kept) / (mi_ms / 1e3), 1),
+            "alg_bytes": mi_bytes, "gbs": round(mi_bytes / (mi_ms * 1e6), 1),
+            "bound": "shared-memory atomics + L1/L2 gathers (chips are re-read from cache)"}
+    except Exception as e:  # noqa: BLE001
+        next_rows["mutual_info"] = {"error": repr(e)}
+
     # ---- end to end: pinned host rasters -> rows on the host -----------------
     e2e = None
     if not args.no_e2e:
@@ -327,6 +349,14 @@ def cuda_arm(args):
         cpu = {"value": m / s, "unit": "matches/s", "cores": os.cpu_count(), "kind": "port",
                "sample": f"1 full {size}x{size} scene pair, default config, one run, {how}",
                "seconds": round(s, 3), "matches": m}
+        if "rows" in next_rows.get("mutual_info", {}):
+            k = min(1500, int(st.n_kept))
+            c4 = [c[:k].cpu().numpy() for c in cols]
+            t0 = time.perf_counter()
+            O.mutual_info(*c4, mon_h, ref_h)
+            dt_mi = time.perf_counter() - t0
+            next_rows["mutual_info"]["cpu_rows_per_sec"] = round(k / dt_mi, 1)
+            next_rows["mutual_info"]["cpu_sample"] = f"{k} rows, oracle.mutual_info (np.histogram2d per row, 1 core)"
 
     if rank == 0:
         line = {
@@ -339,7 +369,7 @@ def cuda_arm(args):
                        "klt": "maxCorners 20000, minDistance 10, blocksize 15, winsize 25, q 0.1, k7, 1 tile",
                        "parallelism": f"scene pairs sharded over {world} GPU(s), no data-path collective",
                        "l2": "inputs (482 MB per pair) exceed the 126 MB L2; no flush needed",
-                       "scenes_per_rank": len(scenes)},
+                       "scenes_per_rank": len(scenes), "pairs_in_flight": args.depth},
             "scene_pairs_per_sec": pairs_per_sec,
             "matches_per_scene": matches / max(1, world * args.steps),
             "roofline": roofline,
@@ -349,6 +379,7 @@ def cuda_arm(args):
             "stages": stages,
             "cpu_baseline": cpu,
             "e2e": e2e,
+            "next_rows": next_rows,
             "gpu_launches": 23 * args.steps * len(sm.windows),
             "clocks": sampler.summary(),
             "stats_last": {k: v for k, v in st.as_dict().items() if k.startswith("n_") or k == "nms_rounds"},

@@ -89,6 +89,10 @@ typedef struct {
     uint32_t nms_rounds;        /* grid-wide rounds the parallel NMS took */
     uint32_t overflow;          /* 1: candidate list exceeded the context capacity */
     uint32_t select_incomplete; /* 1: pre-selection too small; host re-ran with all candidates */
+    uint32_t two_tier;          /* 1: the two-tier corner response produced the corners */
+    uint32_t two_tier_fallback; /* 1: it could not decide (flat image / list overflow) */
+    uint32_t n_border_maxima;   /* two-tier: border / mask-edge pixels checked for the maximum */
+    uint32_t n_exact;           /* two-tier: candidates confirmed in OpenCV's arithmetic */
 } kr_stats;
 
 /* SoA result rows of klt_tracker (klt.py:166-168), capacity >= max corners. */
@@ -115,6 +119,13 @@ KR_API int kr_read_stats(kr_ctx *ctx, void *stream, kr_stats *host_out);
  * subset yields fewer than maxCorners corners, kr_stats.select_incomplete is 1
  * and the caller repeats the call after kr_set_select_all(ctx, 1). */
 KR_API int kr_set_select_all(kr_ctx *ctx, int on);
+
+/* Corner response implementation.  0 (default): two tiers -- integer bounds of
+ * the response at every pixel, OpenCV's float arithmetic only for the masked
+ * maximum and the candidates that survive the value cut-off (falls back to 1 on
+ * its own when it cannot decide); 1: OpenCV's arithmetic at every pixel.  Both
+ * return the same corners. */
+KR_API int kr_set_corner_mode(kr_ctx *ctx, int mode);
 
 /* np.nanmin / np.nanmax of both tiles (klt.py:46) and, when mask_out != NULL,
  * the auto mask (mon != 0) & (ref != 0) & finite & != nodata with its count

@@ -21,7 +21,7 @@ KR_TAIL_NONE, KR_TAIL_AVX512 = 0, 32
 
 EXPORTS = [
     "kr_version", "kr_last_error", "kr_ctx_create", "kr_ctx_destroy", "kr_read_stats",
-    "kr_set_select_all", "kr_minmax_mask", "kr_u8_laplacian", "kr_corner_min_eigen_val",
+    "kr_set_select_all", "kr_set_corner_mode", "kr_minmax_mask", "kr_u8_laplacian", "kr_corner_min_eigen_val",
     "kr_good_features", "kr_pyr_down", "kr_pyr_lk", "kr_klt_track", "kr_zncc", "kr_mutual_info",
     "kr_match_tile",
     "kr_set_profiling", "kr_read_stage_ms",
@@ -47,7 +47,9 @@ class Stats(C.Structure):
                 ("n_candidates", C.c_uint32), ("n_above_threshold", C.c_uint32),
                 ("n_sorted", C.c_uint32), ("n_corners", C.c_uint32), ("n_kept", C.c_uint32),
                 ("nms_rounds", C.c_uint32), ("overflow", C.c_uint32),
-                ("select_incomplete", C.c_uint32)]
+                ("select_incomplete", C.c_uint32), ("two_tier", C.c_uint32),
+                ("two_tier_fallback", C.c_uint32), ("n_border_maxima", C.c_uint32),
+                ("n_exact", C.c_uint32)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -86,6 +88,7 @@ def load_library(path: str = LIB_PATH):
         L.kr_ctx_destroy.restype = None
         L.kr_read_stats.argtypes = [vp, vp, C.POINTER(Stats)]
         L.kr_set_select_all.argtypes = [vp, i32]
+        L.kr_set_corner_mode.argtypes = [vp, i32]
         L.kr_set_profiling.argtypes = [vp, i32]
         L.kr_read_stage_ms.argtypes = [vp, C.POINTER(C.c_float)]
         L.kr_minmax_mask.argtypes = [vp, vp, i64, vp, i64, i32, i32, i32, i32, f64, i32, f64, vp, i64, vp]
@@ -261,6 +264,10 @@ class Context:
 
     def set_select_all(self, on: bool):
         _check(self.lib.kr_set_select_all(self._h, int(bool(on))))
+
+    def set_corner_mode(self, mode: int):
+        """0: two-tier corner response (default); 1: OpenCV's arithmetic at every pixel."""
+        _check(self.lib.kr_set_corner_mode(self._h, int(mode)))
 
     def minmax_mask(self, a, b=None, nodata_a=None, nodata_b=None, want_mask=False):
         h, w = a.shape

@@ -1,7 +1,8 @@
 """Scene-level glue of the hot path: what KariosAPI._compute_matches +
 _handle_klt_results do around the matcher (karios/api/core.py:845-921), minus
-CSV / NMI: per tile KLT._match_tile, then ZNCC for rows with
-score >= confidence_threshold, all in one stream-ordered launch sequence per tile.
+CSV: per tile KLT._match_tile, then ZNCC (and, with_mi, the two mutual-information
+scores) for rows with score >= confidence_threshold, all in one stream-ordered
+launch sequence per tile.
 
     match_pair(mon, ref, mask, conf) -> DataFrame[x0, y0, dx, dy, score, zncc_score]
 
@@ -35,7 +36,8 @@ class SceneMatcher:
     """Workspace + row buffers for scenes up to (h, w); reusable across pairs."""
 
     def __init__(self, h: int, w: int, conf, confidence_threshold: float = 0.4,
-                 tail_mode: int = N.KR_TAIL_AVX512, device=None):
+                 tail_mode: int = N.KR_TAIL_AVX512, device=None, depth: int = 1,
+                 with_mi: bool = False):
         if isinstance(conf.laplacian_kernel_size, str) or conf.laplacian_invert_polarity == "auto":
             raise N.KariosB200Error("SceneMatcher handles fixed kernel size / polarity; "
                                     "use matcher.klt.KLT for the 'auto' searches")
@@ -45,10 +47,21 @@ class SceneMatcher:
         tw, th = min(w, conf.tile_size), min(h, conf.tile_size)
         self.ctx = N.Context(tw, th, int(conf.maxCorners), self.device)
         cap = int(conf.maxCorners) if conf.maxCorners > 0 else self.ctx._cap_unlimited(tw, th)
-        self.rows = N.RowBuffers(cap, self.device, with_zncc=True)
+        self.with_mi = bool(with_mi)
+        self.rows = N.RowBuffers(cap, self.device, with_zncc=True, with_mi=self.with_mi)
         self.kconf = N.make_conf(conf, tail_mode=tail_mode, compute_zncc=True,
-                                 zncc_min_score=confidence_threshold)
+                                 zncc_min_score=confidence_threshold, compute_mi=self.with_mi)
         self.windows = tile_windows(w, h, conf)
+        # extra (context, rows, stream) slots for match_many: tiles of successive
+        # pairs are independent, so `depth` of them are in flight at once and the
+        # latency-bound stages of one (selection, NMS, sorts) overlap the
+        # bandwidth / issue-bound stages of the others
+        self.depth = max(1, int(depth))
+        self._slots = [(self.ctx, self.rows, torch.cuda.Stream(device=self.device))]
+        for _ in range(self.depth - 1):
+            self._slots.append((N.Context(tw, th, int(conf.maxCorners), self.device),
+                                N.RowBuffers(cap, self.device, with_zncc=True, with_mi=self.with_mi),
+                                torch.cuda.Stream(device=self.device)))
 
     def match_device(self, mon: torch.Tensor, ref: torch.Tensor, mask=None, nodata=(None, None),
                      collect=True):
@@ -62,8 +75,63 @@ class SceneMatcher:
                 continue
             total += n
             if collect:
-                tiles.append((self.rows.f32[:, :n].clone(), self.rows.zncc[:n].clone()))
+                t = (self.rows.f32[:, :n].clone(), self.rows.zncc[:n].clone())
+                if self.with_mi:
+                    t = t + (self.rows.mi[:, :n].clone(),)
+                tiles.append(t)
         return tiles, total
+
+    def match_many(self, pairs, mask=None, nodata=(None, None), collect=True):
+        """pairs: iterable of (mon, ref) CUDA tensors.  Every tile of every pair is
+        one unit of work; unit k runs on slot k mod depth (own context, row buffers
+        and stream) and is finalised -- counts read, rows cloned -- only when its
+        slot is needed again, so up to `depth` units overlap on the device.
+        -> (list per pair of per-tile (rows, zncc[, mi]) tuples, total rows)."""
+        results, total = [], 0
+        inflight = [None] * self.depth
+        cur = torch.cuda.current_stream(self.device)
+
+        def finalise(slot):
+            nonlocal total
+            job = inflight[slot]
+            if job is None:
+                return
+            inflight[slot] = None
+            ctx, rows, stream = self._slots[slot]
+            pair_idx, mon, ref, win = job
+            with torch.cuda.stream(stream):
+                st = ctx.read_stats()
+                if st.select_incomplete:          # rare: redo with every candidate
+                    st = ctx.match_tile(mon, ref, mask, win, self.kconf, rows, nodata[0], nodata[1])
+                n = int(st.n_kept)
+                if (mask is None and st.valid == 0) or st.n_corners == 0:
+                    return
+                total += n
+                if collect:
+                    t = (rows.f32[:, :n].clone(), rows.zncc[:n].clone())
+                    if self.with_mi:
+                        t = t + (rows.mi[:, :n].clone(),)
+                    for x in t:
+                        x.record_stream(cur)
+                    results[pair_idx].append(t)
+
+        k = 0
+        for pair_idx, (mon, ref) in enumerate(pairs):
+            results.append([])
+            for win in self.windows:
+                slot = k % self.depth
+                finalise(slot)
+                ctx, rows, stream = self._slots[slot]
+                stream.wait_stream(cur)
+                with torch.cuda.stream(stream):
+                    ctx.match_tile_async(mon, ref, mask, win, self.kconf, rows, nodata[0], nodata[1])
+                inflight[slot] = (pair_idx, mon, ref, win)
+                k += 1
+        for j in range(self.depth):
+            finalise((k + j) % self.depth)
+        for _, _, stream in self._slots:
+            cur.wait_stream(stream)
+        return results, total
 
     @staticmethod
     def to_frame(tiles) -> DataFrame:
@@ -74,10 +142,15 @@ class SceneMatcher:
         z = torch.cat([t[1] for t in tiles]).cpu().numpy()
         df = DataFrame({"x0": f[0], "y0": f[1], "dx": f[2], "dy": f[3], "score": f[4]})
         df["zncc_score"] = z
+        if tiles and len(tiles[0]) > 2:
+            mi = torch.cat([t[2] for t in tiles], dim=1).cpu().numpy()
+            df["mutual_info_score"] = mi[0]         # api/core.py:894-897
+            df["mi_score"] = mi[1]                  # api/core.py:902-907
         return df
 
     def close(self):
-        self.ctx.close()
+        for ctx, _, _ in self._slots:
+            ctx.close()
 
 
 def match_pair(mon, ref, mask, conf, confidence_threshold: float = 0.4, nodata=(None, None),

@@ -149,6 +149,8 @@ KR_API int kr_ctx_create(int device, int max_w, int max_h, int max_corners, kr_c
     A(dev_alloc(&c->d_cand, c->cand_cap));
     A(dev_alloc(&c->d_keys_a, c->cand_cap));
     A(dev_alloc(&c->d_keys_b, c->cand_cap));
+    c->maxlist_cap = c->cand_cap / 4 > 65536 ? c->cand_cap / 4 : 65536;
+    A(dev_alloc(&c->d_maxlist, c->maxlist_cap));
     A(dev_alloc(&c->d_hist, 4096));
     A(dev_alloc(&c->d_xy, c->cand_cap));
     A(dev_alloc(&c->d_state, c->cand_cap));
@@ -198,6 +200,7 @@ KR_API void kr_ctx_destroy(kr_ctx *c)
     cudaFree(c->d_stats);
     for (int i = 0; i < 3; i++) cudaFree(c->d_lut[i]);
     cudaFree(c->d_cand); cudaFree(c->d_keys_a); cudaFree(c->d_keys_b); cudaFree(c->d_hist);
+    cudaFree(c->d_maxlist);
     cudaFree(c->d_xy); cudaFree(c->d_state); cudaFree(c->d_next); cudaFree(c->d_cell_head);
     cudaFree(c->d_mask); cudaFree(c->d_lap[0]); cudaFree(c->d_lap[1]);
     for (int l = 1; l < KR_MAX_LEVELS; l++) { cudaFree(c->d_pyr[0][l]); cudaFree(c->d_pyr[1][l]); }
@@ -210,6 +213,14 @@ KR_API int kr_set_select_all(kr_ctx *ctx, int on)
 {
     if (!ctx) return kr_set_error(KR_ERR_INVALID, "ctx is NULL");
     ctx->force_select_all = on ? 1 : 0;
+    return KR_OK;
+}
+
+KR_API int kr_set_corner_mode(kr_ctx *ctx, int mode)
+{
+    if (!ctx) return kr_set_error(KR_ERR_INVALID, "ctx is NULL");
+    if (mode != 0 && mode != 1) return kr_set_error(KR_ERR_INVALID, "corner mode must be 0 or 1");
+    ctx->no_fast_corners = mode;
     return KR_OK;
 }
 
@@ -259,6 +270,10 @@ KR_API int kr_read_stats(kr_ctx *ctx, void *stream, kr_stats *o)
     o->nms_rounds = h.nms_rounds;
     o->overflow = h.overflow;
     o->select_incomplete = h.select_incomplete;
+    o->two_tier = h.fast_mode;
+    o->two_tier_fallback = h.fast_fallback;
+    o->n_border_maxima = h.n_maxlist;
+    o->n_exact = h.n_exact;
     return KR_OK;
 }
 

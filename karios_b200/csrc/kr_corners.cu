@@ -59,29 +59,6 @@ __host__ inline size_t eig_smem_bytes(const EigGeom &g)
     return hs + pr + eg + px + 64;
 }
 
-// Sobel derivatives (scaled) at one position from its 3x3 neighbourhood, with
-// the exact rounding sequence of the cv2 build.
-__device__ __forceinline__ void sobel_products(float p00, float p01, float p02, float p10, float p12,
-                                               float p20, float p21, float p22, float s, bool tail,
-                                               float &xx, float &xy, float &yy)
-{
-    const float s2 = 2.0f * s;
-    float r0 = p02 - p00, r1 = p12 - p10, r2 = p22 - p20;           // exact (small integers)
-    float dx = __fmaf_rn(s, r0 + r2, __fmul_rn(s2, r1));
-    float t0, t2;
-    if (!tail) {
-        t0 = __fmaf_rn(s, p02, __fmaf_rn(s2, p01, __fmul_rn(s, p00)));
-        t2 = __fmaf_rn(s, p22, __fmaf_rn(s2, p21, __fmul_rn(s, p20)));
-    } else {
-        t0 = __fadd_rn(__fadd_rn(__fmul_rn(s, p00), __fmul_rn(s2, p01)), __fmul_rn(s, p02));
-        t2 = __fadd_rn(__fadd_rn(__fmul_rn(s, p20), __fmul_rn(s2, p21)), __fmul_rn(s, p22));
-    }
-    float dy = __fsub_rn(t2, t0);
-    xx = __fmul_rn(dx, dx);
-    xy = __fmul_rn(dx, dy);
-    yy = __fmul_rn(dy, dy);
-}
-
 // K3.  One block = one EG_TW x EG_TH tile of the tile image.
 //  P0 stage pixels (REFLECT_101)            P1 Sobel products (float32)
 //  P2 horizontal box sums (float64 sliding)  P3 vertical box sums + eigenvalue
@@ -267,13 +244,6 @@ constexpr int EC_RING_F4 = 16 * 2 * 32;          // float4 per warp: 16 rows x (
 __device__ __forceinline__ float i2f_small(int i)
 {
     return __fsub_rn(__int_as_float(0x4B400000 + i), 12582912.0f);
-}
-
-__device__ __forceinline__ float eig_from_sums(double sxx, double sxy, double syy)
-{
-    float a = __fmul_rn((float)sxx, 0.5f), b = (float)sxy, c = __fmul_rn((float)syy, 0.5f);
-    float t = __fsub_rn(a, c);
-    return __fsub_rn(__fadd_rn(a, c), __fsqrt_rn(__fadd_rn(__fmul_rn(t, t), __fmul_rn(b, b))));
 }
 
 // BORDER = the strip touches the left / right image border, the SIMD-tail columns
@@ -604,6 +574,7 @@ k_cutoff(KrDevStats *st, uint32_t *hist, uint32_t target, int select_all)
             if (c2 > cut) cut = c2;
         }
         st->cut_bits = cut;
+        st->cut_applied = (cut != st->thr_bits + 1) ? 1u : 0u;
         st->n_thr = total;
     }
 }
@@ -743,7 +714,10 @@ k_nms(const uint64_t *__restrict__ keys, uint32_t *__restrict__ xy, uint8_t *sta
         st->nms_rounds = round + 1;
         uint32_t nacc = st->n_acc;
         bool enough = (max_corners > 0) && (nacc >= max_corners);
-        if (!enough && st->n_sel < st->n_thr) st->select_incomplete = 1;
+        // the selection was cut short: in the two-tier path n_sel counts exact survivors
+        // and n_thr possible candidates, so the cut itself is the criterion there
+        const bool cut_short = st->fast_mode ? (st->cut_applied != 0) : (st->n_sel < st->n_thr);
+        if (!enough && cut_short) st->select_incomplete = 1;
         st->undecided[0] = st->undecided[1] = st->undecided[2] = 0;
     }
 }
@@ -757,7 +731,7 @@ __global__ void k_accept_all(const uint64_t *__restrict__ keys, uint64_t *__rest
         accepted[i] = keys[i];
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         st->n_acc = n;
-        if (st->n_sel < st->n_thr) st->select_incomplete = 1;
+        if (st->fast_mode ? (st->cut_applied != 0) : (st->n_sel < st->n_thr)) st->select_incomplete = 1;
     }
 }
 
@@ -786,7 +760,12 @@ __global__ void k_clear_counts(KrDevStats *st)
     st->eig_max_enc = KR_ENC_NEG_INF;
     st->select_incomplete = 0;
     st->nms_rounds = 0;
+    st->lmax_enc = st->umax_enc = KR_ENC_NEG_INF;
+    st->n_maxlist = st->n_exact = 0;
+    st->cut_applied = st->fast_mode = st->fast_fallback = 0;
 }
+
+__global__ void k_set_fast_mode(KrDevStats *st) { st->fast_mode = 1; }
 
 }  // namespace
 
@@ -818,7 +797,16 @@ int krl_good_features(kr_ctx *ctx, const uint8_t *img, int64_t pitch, const uint
 
     k_clear_counts<<<1, 1, 0, s>>>(ctx->d_stats);
     KR_LAUNCH_CHECK();
-    if (block == 15 && w >= 16 && h >= 16) {
+    // two-tier response: integer bounds for every pixel, OpenCV's arithmetic only where
+    // the answer depends on it (kr_corner_fast.cu); needs a bounded maxCorners
+    const bool fast = block == 15 && w >= 16 && h >= 16 && emit && !eig_out && !select_all &&
+                      max_corners > 0 && !ctx->no_fast_corners && pitch < (1ll << 31) &&
+                      mask_pitch < (1ll << 31);
+    if (fast) {
+        k_set_fast_mode<<<1, 1, 0, s>>>(ctx->d_stats);
+        KR_LAUNCH_CHECK();
+        KR_TRY(krl_eig_fast(ctx, img, pitch, mask, mask_pitch, w, h, scale, tail_start, s));
+    } else if (block == 15 && w >= 16 && h >= 16) {
         const size_t esm = (size_t)EC_WARPS * (EC_RING_F4 * 16 + EC_CBUF * 8);
         static bool ec_set = false;
         if (!ec_set) {
@@ -871,15 +859,27 @@ int krl_good_features(kr_ctx *ctx, const uint8_t *img, int64_t pitch, const uint
 
     const uint32_t cap = (uint32_t)ctx->cand_cap;
     const int sgrid = ctx->num_sms * 4;
-    k_cand_hist<<<sgrid, 256, 0, s>>>(ctx->d_cand, ctx->d_stats, ctx->d_hist, quality, cap);
-    KR_LAUNCH_CHECK();
+    if (fast) {
+        KR_TRY(krl_cand_hist_fast(ctx, quality, scale, s));
+    } else {
+        k_cand_hist<<<sgrid, 256, 0, s>>>(ctx->d_cand, ctx->d_stats, ctx->d_hist, quality, cap);
+        KR_LAUNCH_CHECK();
+    }
     uint32_t target = 0;
     if (max_corners <= 0) select_all = 1;
     else target = 2u * (uint32_t)max_corners + 4096u;
     k_cutoff<<<1, 1024, 0, s>>>(ctx->d_stats, ctx->d_hist, target, select_all);
     KR_LAUNCH_CHECK();
-    k_select<<<sgrid, 256, 0, s>>>(ctx->d_cand, ctx->d_keys_a, ctx->d_stats, cap, cap);
-    KR_LAUNCH_CHECK();
+    if (fast) {
+        // possible candidates above the cut -> exact verdicts and exact keys
+        k_select<<<sgrid, 256, 0, s>>>(ctx->d_cand, ctx->d_keys_b, ctx->d_stats, cap, cap);
+        KR_LAUNCH_CHECK();
+        KR_TRY(krl_exact_cands(ctx, img, pitch, w, h, scale, tail_start, quality, (int)(target + target / 4),
+                               ctx->d_keys_b, ctx->d_keys_a, s));
+    } else {
+        k_select<<<sgrid, 256, 0, s>>>(ctx->d_cand, ctx->d_keys_a, ctx->d_stats, cap, cap);
+        KR_LAUNCH_CHECK();
+    }
     KR_MARK(ctx, 5, s);
 
     if (min_distance >= 1.0) {

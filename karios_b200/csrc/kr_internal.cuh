@@ -2,6 +2,7 @@
 // Layout of the library:
 //   kr_prep.cu     K1 min/max + auto mask, LUT build, K2 normalise + Laplacian
 //   kr_corners.cu  K3 min-eigenvalue response + candidates, K4 selection (NMS)
+//   kr_corner_fast.cu  K3 in two tiers: integer bounds everywhere, exact values where needed
 //   kr_sort.cu     chunk bitonic sort + rank merge (u64 keys)
 //   kr_lk.cu       K5 pyrDown, K6 pyramidal LK (forward + backward + back-check)
 //   kr_zncc.cu     K7 ZNCC
@@ -27,7 +28,12 @@ struct KrDevStats {
     uint32_t undecided[3];
     uint32_t barrier[2];
     uint32_t n_rowkeys;
-    uint32_t pad[3];
+    // two-tier corner response (kr_corner_fast.cu)
+    uint32_t lmax_enc, umax_enc;        // bounds of the masked maximum, integer units
+    uint32_t n_maxlist, n_exact;
+    uint32_t cut_applied;               // the value cut-off dropped candidates above the threshold
+    uint32_t fast_mode, fast_fallback;  // two-tier path in use / it cannot decide: re-run exactly
+    uint32_t pad[2];
 };
 
 struct kr_ctx {
@@ -40,6 +46,8 @@ struct kr_ctx {
     uint64_t *d_cand;       // K3 output: (float bits << 32) | (y*W + x)
     uint64_t *d_keys_a;     // selected keys / sort ping
     uint64_t *d_keys_b;     // accepted keys / sort pong
+    uint64_t *d_maxlist;    // two-tier K3: pixels that may hold the masked maximum
+    int64_t maxlist_cap;
     uint32_t *d_hist;       // 4096-bin value histogram of the candidates
     uint32_t *d_xy;         // per selected candidate: x | y << 16
     uint8_t *d_state;       // NMS state per selected candidate
@@ -58,6 +66,7 @@ struct kr_ctx {
     uint8_t *d_keep;
     int nms_grid;           // co-resident grid of the persistent NMS kernel
     int force_select_all;   // sort every candidate above the threshold (no pre-selection)
+    int no_fast_corners;    // always use the one-tier exact response kernel (kr_set_corner_mode)
     int last_dtype;         // dtype of the last min/max pass (for kr_read_stats)
     int prof_on;            // stage events enabled (kr_set_profiling)
     cudaEvent_t ev[KR_NUM_STAGES + 1];
@@ -115,6 +124,37 @@ __host__ __device__ __forceinline__ float kr_f32_dec_bits(uint32_t e, int)
 }
 #define KR_ENC_NEG_INF 0x007fffffu   /* kr_f32_enc(-inf) */
 
+// Sobel derivatives (scaled) at one position from its 3x3 neighbourhood, with
+// the exact rounding sequence of the cv2 build.
+__device__ __forceinline__ void sobel_products(float p00, float p01, float p02, float p10, float p12,
+                                               float p20, float p21, float p22, float s, bool tail,
+                                               float &xx, float &xy, float &yy)
+{
+    const float s2 = 2.0f * s;
+    float r0 = p02 - p00, r1 = p12 - p10, r2 = p22 - p20;           // exact (small integers)
+    float dx = __fmaf_rn(s, r0 + r2, __fmul_rn(s2, r1));
+    float t0, t2;
+    if (!tail) {
+        t0 = __fmaf_rn(s, p02, __fmaf_rn(s2, p01, __fmul_rn(s, p00)));
+        t2 = __fmaf_rn(s, p22, __fmaf_rn(s2, p21, __fmul_rn(s, p20)));
+    } else {
+        t0 = __fadd_rn(__fadd_rn(__fmul_rn(s, p00), __fmul_rn(s2, p01)), __fmul_rn(s, p02));
+        t2 = __fadd_rn(__fadd_rn(__fmul_rn(s, p20), __fmul_rn(s2, p21)), __fmul_rn(s, p22));
+    }
+    float dy = __fsub_rn(t2, t0);
+    xx = __fmul_rn(dx, dx);
+    xy = __fmul_rn(dx, dy);
+    yy = __fmul_rn(dy, dy);
+}
+
+// calcMinEigenVal on the float64 box sums: plain float32, no contraction.
+__device__ __forceinline__ float eig_from_sums(double sxx, double sxy, double syy)
+{
+    float a = __fmul_rn((float)sxx, 0.5f), b = (float)sxy, c = __fmul_rn((float)syy, 0.5f);
+    float t = __fsub_rn(a, c);
+    return __fsub_rn(__fadd_rn(a, c), __fsqrt_rn(__fadd_rn(__fmul_rn(t, t), __fmul_rn(b, b))));
+}
+
 // ---- stage launchers (each enqueues on `s`, returns a kr_status) -----------
 int krl_reset_stats(kr_ctx *ctx, cudaStream_t s);
 int krl_minmax_mask(kr_ctx *ctx, const void *a, int64_t pa, const void *b, int64_t pb, int dtype,
@@ -160,3 +200,9 @@ int krl_mutual_info(const void *ref, int64_t rp, int rw, int rh, const void *mon
                     int mh, int dtype, const float *x0, const float *y0, const float *dx,
                     const float *dy, const float *score, float min_score, int n,
                     const uint32_t *d_count, double *out_studholme, double *out_nmi, cudaStream_t s);
+int krl_eig_fast(kr_ctx *ctx, const uint8_t *img, int64_t pitch, const uint8_t *mask, int64_t mask_pitch,
+                 int w, int h, float scale, int tail_start, cudaStream_t s);
+int krl_cand_hist_fast(kr_ctx *ctx, double quality, float scale, cudaStream_t s);
+int krl_exact_cands(kr_ctx *ctx, const uint8_t *img, int64_t pitch, int w, int h, float scale,
+                    int tail_start, double quality, int expected, const uint64_t *sel, uint64_t *keys,
+                    cudaStream_t s);

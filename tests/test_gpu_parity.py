@@ -147,6 +147,48 @@ def test_good_features_parameter_sweep(golden, N, ctx):
     assert ctx.good_features(dev(lap), dev(np.zeros_like(lap)), 100, 0.1, 10, 15).shape[0] == 0
 
 
+def test_corner_modes_agree(golden, N):
+    """The two-tier corner response (integer bounds + exact values where needed) and
+    OpenCV's arithmetic at every pixel return the same corners in the same order:
+    golden Laplacians, noise, saturated / flat images, masks, image borders."""
+    from karios_b200 import synth
+    rng = np.random.default_rng(17)
+    imgs = []
+    for name in CASES:
+        g = golden(name)
+        imgs.append((g["lap_ref"], g["mask_box"]))
+    imgs.append((rng.integers(0, 256, (333, 517)).astype(np.uint8), None))
+    flat = np.zeros((260, 300), np.uint8)
+    flat[60:130, 70:200] = 255
+    flat[180:, :] = rng.integers(0, 3, (80, 300))
+    flat[:40, 250:] = rng.integers(0, 256, (40, 50))
+    imgs.append((flat, None))
+    imgs.append((np.full((100, 140), 7, np.uint8), None))                 # nothing to find
+    m = (rng.random((333, 517)) > 0.3).astype(np.uint8)
+    m[:, :40] = 0
+    imgs.append((imgs[3][0], m))
+    ref_t, _ = synth.make_pair(700, 900, seed=5)
+    big = O.laplacian(O.to_uint8(ref_t.view(torch.int16).numpy().view(np.uint16)), 7)
+    imgs.append((big, None))
+    edge = rng.integers(0, 40, (200, 240)).astype(np.uint8)               # strongest response on the border
+    edge[:3, :] = 255
+    edge[:, -2:] = 255
+    imgs.append((edge, None))
+    c = N.Context(1024, 1024, 5000)
+    try:
+        for k, (img, mask) in enumerate(imgs):
+            for mc, q, md in ((5000, 0.1, 10), (40, 0.01, 3), (700, 0.3, 1.5), (200, 1e-5, 6)):
+                d_img = dev(img)
+                d_mask = None if mask is None else dev(mask)
+                c.set_corner_mode(1)
+                want = c.good_features(d_img, d_mask, mc, q, md, 15).cpu().numpy()
+                c.set_corner_mode(0)
+                got = c.good_features(d_img, d_mask, mc, q, md, 15).cpu().numpy()
+                assert got.shape == want.shape and np.array_equal(got, want), (k, mc, q, md, got.shape, want.shape)
+    finally:
+        c.close()
+
+
 @pytest.mark.parametrize("name", CASES)
 def test_pyr_down(golden, N, ctx, name):
     g = golden(name)
