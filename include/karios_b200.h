@@ -214,6 +214,41 @@ KR_API int kr_match_tile(kr_ctx *ctx, const void *mon, int64_t mon_pitch, const 
                          int has_nodata_mon, double nodata_mon, int has_nodata_ref,
                          double nodata_ref, const kr_klt_conf *conf, kr_rows rows, void *stream);
 
+/* ---- full-frame passes either side of the matching path; these
+ * take no context. ---- */
+
+/* Element-wise steps of skimage.registration.phase_cross_correlation(mon, ref)
+ * (upsample_factor 1, normalization "phase") as LargeOffsetMatcher.match calls it
+ * (karios/matcher/large_offset.py:32-41).  a, b: interleaved complex spectra of n
+ * elements (float32 or float64 pairs).  a <- a conj(b) / max(|a conj(b)|, 100 eps). */
+KR_API int kr_cross_power(void *a, const void *b, int64_t n, int is_double, void *stream);
+
+/* np.argmax(np.abs(x)) over n real values: first index of the maximum -> *out_index
+ * (device int64).  scratch16: 16 bytes of device scratch. */
+KR_API int kr_argmax_abs(const void *x, int64_t n, int is_double, void *scratch16, int64_t *out_index,
+                         void *stream);
+
+/* shift_image(img, y_off, x_off) (karios/core/image.py:70-101): dst[y][x] =
+ * src[y + y_off][x + x_off], zero where that leaves the raster.  dst != src. */
+KR_API int kr_shift_image(const void *src, int64_t src_pitch, void *dst, int64_t dst_pitch, int dtype,
+                          int w, int h, int x_off, int y_off, void *stream);
+
+/* Value histogram of an integer raster over [lo, lo + nbins), nbins <= 8192 per call,
+ * ADDED to hist[nbins] (device uint64): np.nanpercentile(image, [2, 98]) of
+ * KariosAPI._check_quality (karios/api/core.py:500-506) is read off it. */
+KR_API int kr_histogram(const void *img, int64_t pitch, int dtype, int w, int h, int lo, int nbins,
+                        uint64_t *hist, void *stream);
+
+/* np.count_nonzero(image) with image[mask == 0] = 0 when a mask is given
+ * (karios/api/core.py:285-290) -> *d_count (device uint64). */
+KR_API int kr_count_valid(const void *img, int64_t pitch, int dtype, int w, int h, const uint8_t *mask,
+                          int64_t mask_pitch, uint64_t *d_count, void *stream);
+
+/* image.array[y0.astype(int), x0.astype(int)] as float64 (NaN outside the raster):
+ * _filter_by_dn_values (karios/api/core.py:687-728), DEM altitudes (:1050-1053). */
+KR_API int kr_gather_points(const void *img, int64_t pitch, int dtype, int w, int h, const float *x0,
+                            const float *y0, int n, double *out, void *stream);
+
 /* Measurement hooks (no reference counterpart).  With profiling on, kr_match_tile
  * brackets its stages with CUDA events on the caller's stream; after the stream
  * has been synchronised kr_read_stage_ms returns the KR_NUM_STAGES durations

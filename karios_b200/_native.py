@@ -25,6 +25,8 @@ EXPORTS = [
     "kr_good_features", "kr_pyr_down", "kr_pyr_lk", "kr_klt_track", "kr_zncc", "kr_mutual_info",
     "kr_match_tile",
     "kr_set_profiling", "kr_read_stage_ms",
+    "kr_cross_power", "kr_argmax_abs", "kr_shift_image", "kr_histogram", "kr_count_valid",
+    "kr_gather_points",
 ]
 NUM_STAGES = 12
 STAGE_NAMES = ["minmax_mask", "laplacian_mon", "laplacian_ref", "corner_response", "select",
@@ -107,6 +109,12 @@ def load_library(path: str = LIB_PATH):
                                      vp, vp, vp, vp]
         L.kr_match_tile.argtypes = [vp, vp, i64, vp, i64, i32, i32, i32, vp, i64, i32, i32, i32, i32,
                                     i32, f64, i32, f64, C.POINTER(KltConf), Rows, vp]
+        L.kr_cross_power.argtypes = [vp, vp, i64, i32, vp]
+        L.kr_argmax_abs.argtypes = [vp, i64, i32, vp, vp, vp]
+        L.kr_shift_image.argtypes = [vp, i64, vp, i64, i32, i32, i32, i32, i32, vp]
+        L.kr_histogram.argtypes = [vp, i64, i32, i32, i32, i32, i32, vp, vp]
+        L.kr_count_valid.argtypes = [vp, i64, i32, i32, i32, vp, i64, vp, vp]
+        L.kr_gather_points.argtypes = [vp, i64, i32, i32, i32, vp, vp, i32, vp, vp]
         for name in EXPORTS:
             if name not in ("kr_last_error", "kr_ctx_destroy", "kr_version"):
                 getattr(L, name).restype = i32
@@ -408,3 +416,80 @@ class Context:
             self.set_select_all(True)
         self.set_select_all(False)
         return st
+
+
+# ---- context-free entry points (full-frame passes around the matching path) ------
+def _require_cuda():
+    if not torch.cuda.is_available():
+        raise KariosB200Error("no CUDA device: karios_b200 has no CPU fallback")
+    return load_library()
+
+
+def cross_power_(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+    """In place: a <- a conj(b) / max(|a conj(b)|, 100 eps) on complex CUDA tensors."""
+    lib = _require_cuda()
+    if a.dtype != b.dtype or a.shape != b.shape or a.dtype not in (torch.complex64, torch.complex128):
+        raise KariosB200Error("cross_power_ needs two complex tensors of one dtype and shape")
+    if not (a.is_contiguous() and b.is_contiguous()):
+        raise KariosB200Error("cross_power_ needs contiguous tensors")
+    _check(lib.kr_cross_power(a.data_ptr(), b.data_ptr(), a.numel(), int(a.dtype == torch.complex128),
+                              _stream()))
+    return a
+
+
+def argmax_abs(x: torch.Tensor) -> torch.Tensor:
+    """First index of max |x| (np.argmax(np.abs(x))) -> device int64 tensor [1]."""
+    lib = _require_cuda()
+    if x.dtype not in (torch.float32, torch.float64) or not x.is_contiguous():
+        raise KariosB200Error("argmax_abs needs a contiguous float32 / float64 tensor")
+    scratch = torch.empty(2, dtype=torch.int64, device=x.device)
+    out = torch.empty(1, dtype=torch.int64, device=x.device)
+    _check(lib.kr_argmax_abs(x.data_ptr(), x.numel(), int(x.dtype == torch.float64), scratch.data_ptr(),
+                             out.data_ptr(), _stream()))
+    return out
+
+
+def shift_image(img: torch.Tensor, y_off=0, x_off=0) -> torch.Tensor:
+    """shift_image (karios/core/image.py:70-101) on a CUDA raster: a new tensor."""
+    lib = _require_cuda()
+    y_off, x_off = int(round(y_off)), int(round(x_off))
+    h, w = img.shape
+    out = torch.empty_like(img)
+    _check(lib.kr_shift_image(img.data_ptr(), _pitch(img), out.data_ptr(), _pitch(out), dtype_code(img),
+                              w, h, x_off, y_off, _stream()))
+    return out
+
+
+def histogram(img: torch.Tensor, lo: int, hi: int) -> torch.Tensor:
+    """Counts of the integer values lo..hi (inclusive) -> device int64 tensor [hi - lo + 1]."""
+    lib = _require_cuda()
+    h, w = img.shape
+    n = int(hi) - int(lo) + 1
+    hist = torch.zeros(n, dtype=torch.int64, device=img.device)
+    for start in range(0, n, 8192):
+        nb = min(8192, n - start)
+        _check(lib.kr_histogram(img.data_ptr(), _pitch(img), dtype_code(img), w, h, int(lo) + start, nb,
+                                hist[start:].data_ptr(), _stream()))
+    return hist
+
+
+def count_valid(img: torch.Tensor, mask=None) -> int:
+    lib = _require_cuda()
+    h, w = img.shape
+    out = torch.zeros(1, dtype=torch.int64, device=img.device)
+    _check(lib.kr_count_valid(img.data_ptr(), _pitch(img), dtype_code(img), w, h,
+                              mask.data_ptr() if mask is not None else None,
+                              _pitch(mask) if mask is not None else 0, out.data_ptr(), _stream()))
+    return int(out.item())
+
+
+def gather_points(img: torch.Tensor, x0: torch.Tensor, y0: torch.Tensor) -> torch.Tensor:
+    """img[int(y0), int(x0)] as float64 (NaN outside the raster)."""
+    lib = _require_cuda()
+    h, w = img.shape
+    n = x0.shape[0]
+    out = torch.empty(n, dtype=torch.float64, device=img.device)
+    if n:
+        _check(lib.kr_gather_points(img.data_ptr(), _pitch(img), dtype_code(img), w, h, x0.data_ptr(),
+                                    y0.data_ptr(), n, out.data_ptr(), _stream()))
+    return out

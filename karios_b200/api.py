@@ -220,3 +220,136 @@ class ScenePipeline:
 
     def close(self):
         self.sm.close()
+
+
+# ---------------------------------------------------------------------------
+# Scene-level passes of KariosAPI around the matcher
+def _dev_raster(img, dev):
+    full = getattr(img, "device_array", None)
+    if full is not None:
+        return full
+    return N.to_device(img.array if hasattr(img, "array") else img, dev)
+
+
+def percentiles_2_98(raster) -> np.ndarray:
+    """np.nanpercentile(image.array, [2, 98]) of an integer raster
+    (KariosAPI._check_quality, karios/api/core.py:500-506): one device histogram,
+    then NumPy's 'linear' rule on the two order statistics."""
+    dev = torch.device("cuda", torch.cuda.current_device())
+    t = _dev_raster(raster, dev)
+    info = {torch.uint8: (0, 255), torch.uint16: (0, 65535), torch.int16: (-32768, 32767)}
+    if t.dtype not in info:
+        raise N.KariosB200Error("percentiles need an integer raster (uint8, uint16, int16)")
+    lo, hi = info[t.dtype]                           # full value range: 8 passes of 8192 bins for 16 bits
+    cum = torch.cumsum(N.histogram(t, lo, hi), 0).cpu().numpy()
+    n = int(cum[-1])
+    out = []
+    for q in (np.float64(2) / 100, np.float64(98) / 100):
+        virtual = n * q + (1 + q * (1 - 1 - 1)) - 1          # numpy _compute_virtual_index, alpha = beta = 1
+        prev = np.floor(virtual)
+        gamma = virtual - prev
+        k0 = int(prev)
+        k1 = min(k0 + 1, n - 1)
+        a = np.float64(lo + int(np.searchsorted(cum, k0 + 1, side="left")))
+        b = np.float64(lo + int(np.searchsorted(cum, k1 + 1, side="left")))
+        diff = b - a
+        out.append(a + diff * gamma if gamma < 0.5 else b - diff * (1 - gamma))   # numpy _lerp
+    return np.array(out)
+
+
+def check_quality(monitored_image, reference_image) -> dict:
+    """KariosAPI._check_quality (api/core.py:491-506): dynamic range between the 2nd
+    and 98th percentile, flagged low when <= 10."""
+    res = {}
+    for name, img in (("monitored", monitored_image), ("reference", reference_image)):
+        mm = percentiles_2_98(img)
+        res[name] = {"p2": float(mm[0]), "p98": float(mm[1]), "low_dynamic": bool(mm[1] - mm[0] <= 10)}
+    return res
+
+
+def count_valid_pixels(monitored_image, mask=None) -> int:
+    """np.count_nonzero of the monitored image with masked-out pixels zeroed
+    (KariosAPI.analyze_accuracy, api/core.py:285-290)."""
+    dev = torch.device("cuda", torch.cuda.current_device())
+    m = None if mask is None else _dev_raster(mask, dev)
+    if m is not None and m.dtype != torch.uint8:
+        m = (m != 0).to(torch.uint8)
+    return N.count_valid(_dev_raster(monitored_image, dev), m)
+
+
+def _point_values(points: DataFrame, raster):
+    dev = torch.device("cuda", torch.cuda.current_device())
+    x = torch.from_numpy(np.array(points["x0"].to_numpy(np.float32), copy=True)).to(dev)
+    y = torch.from_numpy(np.array(points["y0"].to_numpy(np.float32), copy=True)).to(dev)
+    return N.gather_points(_dev_raster(raster, dev), x, y).cpu().numpy()
+
+
+def filter_by_dn_values(points: DataFrame, monitored_image, reference_image, no_values=None) -> DataFrame:
+    """KariosAPI._filter_by_dn_values (api/core.py:655-744): drop key points whose
+    pixel (int(y0), int(x0)) holds an excluded DN in either image or an image's own
+    no-data value."""
+    ref_nd = getattr(reference_image, "no_data_value", None)
+    mon_nd = getattr(monitored_image, "no_data_value", None)
+    if not no_values and ref_nd is None and mon_nd is None:
+        return points
+    if len(points) == 0:
+        return points
+    ref_values = _point_values(points, reference_image)
+    mon_values = _point_values(points, monitored_image)
+    keep = np.ones(len(points), dtype=bool)
+    for no_value in no_values or []:
+        keep &= ~((ref_values == no_value) | (mon_values == no_value))
+    if ref_nd is not None:
+        keep &= ~(ref_values == ref_nd)
+    if mon_nd is not None:
+        keep &= ~(mon_values == mon_nd)
+    return points[keep].copy()
+
+
+def dem_altitudes(points: DataFrame, dem) -> np.ndarray:
+    """dem.array[int(y0), int(x0)] per key point (api/core.py:1050-1053)."""
+    vals = _point_values(points, dem)
+    src = getattr(dem, "device_array", None)
+    dt = src.dtype if src is not None else getattr(getattr(dem, "array", dem), "dtype", None)
+    if dt in (torch.float32, np.dtype(np.float32)):
+        return vals.astype(np.float32)
+    return vals
+
+
+def altitude_profile(values, altitudes, bin_size: int = 100):
+    """mean_profile (karios/report/commons.py:49-71) of `values` grouped by altitude
+    bins: (bin centres int32, count, mean, std with ddof = 1) -- O(N) on <= maxCorners
+    rows, NumPy on the host like the reference's pandas groupby."""
+    values = np.asarray(values, np.float64)
+    group = np.floor_divide(np.asarray(altitudes), bin_size)
+    keys = np.unique(group)
+    centres = (keys * bin_size + bin_size // 2).astype(np.int32)
+    cnt = np.array([np.sum(group == k) for k in keys])
+    mean = np.array([values[group == k].mean() for k in keys])
+    std = np.array([values[group == k].std(ddof=1) if np.sum(group == k) > 1 else np.nan for k in keys])
+    return centres, cnt, mean, std
+
+
+def match_pair_large_shift(mon, ref, mask, conf, offset_threshold: float, confidence_threshold: float = 0.4):
+    """KariosAPI.match_images with enable_large_shift_detection (api/core.py:233-252,
+    746-786): whole-pixel offsets from the phase correlation, each axis applied only
+    when |offset| >= threshold, KLT on the shifted monitored raster, offsets added back
+    to dx / dy, no ZNCC once a shift was applied (api/core.py:876).
+    -> (DataFrame, (x_offset, y_offset) applied or None)"""
+    from karios_b200.core.image import shift_image
+    from karios_b200.matcher.large_offset import phase_cross_correlation_shift
+    dev = torch.device("cuda", torch.cuda.current_device())
+    mon_t, ref_t = N.to_device(mon, dev), N.to_device(ref, dev)
+    offsets = phase_cross_correlation_shift(mon_t, ref_t)
+    if abs(offsets[1]) < offset_threshold:
+        offsets[1] = 0
+    if abs(offsets[0]) < offset_threshold:
+        offsets[0] = 0
+    if offsets[0] == 0 and offsets[1] == 0:
+        return match_pair(mon_t, ref_t, mask, conf, confidence_threshold), None
+    shifted = shift_image(mon_t, x_off=offsets[1], y_off=offsets[0])
+    df = match_pair(shifted, ref_t, mask, conf, confidence_threshold)
+    df["dx"] = df["dx"] + offsets[1]
+    df["dy"] = df["dy"] + offsets[0]
+    df["zncc_score"] = np.nan
+    return df, (offsets[1], offsets[0])

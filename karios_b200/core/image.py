@@ -39,3 +39,18 @@ class DeviceRaster(ArrayRaster):
         self.no_data_value = no_data_value
         self.y_size, self.x_size = t.shape
         self.filepath = filepath
+
+
+def shift_image(img, y_off=0, x_off=0):
+    """shift_image (karios/core/image.py:70-101): whole-pixel shift, shape kept, zeros
+    where the source leaves the raster.  A CUDA tensor gives a CUDA tensor; a NumPy
+    array is uploaded, shifted on the device (kr_shift_image) and returned as NumPy."""
+    from karios_b200 import _native as N
+    if isinstance(img, torch.Tensor):
+        return N.shift_image(img, y_off, x_off)
+    dev = torch.device("cuda", torch.cuda.current_device())
+    arr = np.asarray(img)
+    out = N.shift_image(N.to_device(arr, dev), y_off, x_off).cpu()
+    if arr.dtype == np.uint16:
+        return out.view(torch.int16).numpy().view(np.uint16)
+    return out.numpy()

@@ -38,7 +38,7 @@
 
 namespace {
 
-constexpr int FA_WARPS = 4, FA_BLOCKS_PER_SM = 3, FA_OUTW = 104, FA_LEFT = 12, FA_CBUF = 256;
+constexpr int FA_WARPS = 4, FA_BLOCKS_PER_SM = 4, FA_OUTW = 104, FA_LEFT = 12, FA_CBUF = 256;
 constexpr int FA_RING_I4 = 16 * 32;              // uint4 per warp: 16 rows x 32 lanes of (Dx | Dy << 16) x 4
 constexpr float FA_K1 = 0.04f;                   // >= 1.5 x 64 d, d = 7000 * 2^-24 (Sobel rounding)
 constexpr float FA_K2 = 1.9073486328125e-6f;     // 2^-19 >= 13 * 2^-24 (products, formula, tier-1 float32)
@@ -231,7 +231,7 @@ __device__ __forceinline__ void approx_body(
             const bool mq = row_in && col_in[j] && (!HAS_MASK || ((mkq >> (8 * j)) & 255u) != 0);
             L0[j + 1] = mq ? lam - E : NEG_INF;
             // X == 0: every product of the window vanishes and so does OpenCV's value
-            N.U[j] = (mq && col_ok[j] && X != 0 && u > 0.f) ? u : QNAN;
+            N.U[j] = (mq && col_ok[j] && X != 0) ? u : QNAN;      // X >= 1 => u >= K0 > 0
         }
         // (the outermost lanes have no neighbours for the 15-column sums: not pixels of this warp)
 #pragma unroll
@@ -399,10 +399,20 @@ k_eig_approx(const uint8_t *__restrict__ img, uint32_t pitch, const uint8_t *__r
 constexpr int EX_WARPS = 4;
 
 template <int NB> struct ExSmem {
-    float prod[3 * (14 + NB) * (14 + NB)];
     double col[3 * NB * (14 + NB)];
-    uint8_t pix[(16 + NB) * (16 + NB) + 8];
+    float prod[3 * (14 + NB) * (14 + NB)];
+    float pix[(16 + NB) * (16 + NB) + 3];
+    int rowoff[16 + NB], coloff[16 + NB];        // REFLECT_101 pixel coordinates of the patch
+    int rsy[14 + NB], csx[14 + NB];              // neighbour strides (sign = mirrored), bit 30 of csx = SIMD tail
 };
+
+__device__ __forceinline__ double shfl_f64(double v, int src)
+{
+    int lo = __double2loint(v), hi = __double2hiint(v);
+    lo = __shfl_sync(0xffffffffu, lo, src);
+    hi = __shfl_sync(0xffffffffu, hi, src);
+    return __hiloint2double(hi, lo);
+}
 
 template <int NB>
 __device__ __forceinline__ void exact_values(const uint8_t *__restrict__ img, int64_t pitch, int w, int h,
@@ -413,28 +423,38 @@ __device__ __forceinline__ void exact_values(const uint8_t *__restrict__ img, in
     const int oy = y - 7 - NB / 2, ox = x - 7 - NB / 2;         // product region origin (virtual)
     float *prod = sm.prod;
     double *col = sm.col;                                        // [3][NB][R]
-    uint8_t *pix = sm.pix;                                       // virtual patch, REFLECT_101 pixels
+    float *pix = sm.pix;                                         // virtual patch, REFLECT_101 pixels
+    if (lane < PW) {
+        sm.rowoff[lane] = kr_reflect101(oy - 1 + lane, h);
+        sm.coloff[lane] = kr_reflect101(ox - 1 + lane, w);
+    }
+    if (lane < R) {
+        // box-filter border: the product AT the REFLECT_101 position, i.e. with the
+        // neighbour roles of the mirrored patch swapped back
+        const int gy = oy + lane, gx = ox + lane;
+        sm.rsy[lane] = (gy < 0 || gy >= h) ? -PW : PW;
+        sm.csx[lane] = ((gx < 0 || gx >= w) ? -1 : 1) * ((kr_reflect101(gx, w) >= tail_start) ? 2 : 1);
+    }
+    __syncwarp();
     for (int t = lane; t < PW * PW; t += 32) {
         const int py = t / PW, px = t - py * PW;
-        pix[t] = __ldg(img + (int64_t)kr_reflect101(oy - 1 + py, h) * pitch + kr_reflect101(ox - 1 + px, w));
+        pix[t] = (float)__ldg(img + (int64_t)sm.rowoff[py] * pitch + sm.coloff[px]);
     }
     __syncwarp();
     for (int t = lane; t < R * R; t += 32) {
         const int ty = t / R, tx = t - ty * R;
-        const int gy = oy + ty, gx = ox + tx;
-        // box-filter border: the product AT the REFLECT_101 position, i.e. with the
-        // neighbour roles of the mirrored patch swapped back
-        const int sy = (gy < 0 || gy >= h) ? -PW : PW, sx = (gx < 0 || gx >= w) ? -1 : 1;
-        const uint8_t *c = pix + (ty + 1) * PW + (tx + 1);
+        const int sy = sm.rsy[ty], cx2 = sm.csx[tx];
+        const bool tail = cx2 == 2 || cx2 == -2;
+        const int sx = cx2 > 0 ? 1 : -1;
+        const float *c = pix + (ty + 1) * PW + (tx + 1);
         float xx, xy, yy;
-        sobel_products((float)c[-sy - sx], (float)c[-sy], (float)c[-sy + sx], (float)c[-sx], (float)c[sx],
-                       (float)c[sy - sx], (float)c[sy], (float)c[sy + sx], s,
-                       kr_reflect101(gx, w) >= tail_start, xx, xy, yy);
+        sobel_products(c[-sy - sx], c[-sy], c[-sy + sx], c[-sx], c[sx], c[sy - sx], c[sy], c[sy + sx], s,
+                       tail, xx, xy, yy);
         prod[t] = xx; prod[R * R + t] = xy; prod[2 * R * R + t] = yy;
     }
     __syncwarp();
-    // column sums of 15 rows for every (column, vertical offset), then 15 columns
-    // per window; float64 sums of float32 products are exact
+    // column sums of 15 rows for every (channel, vertical offset, column), then 15
+    // columns per window; float64 sums of float32 products are exact
     for (int t = lane; t < 3 * NB * R; t += 32) {
         const int ch = t / (NB * R), rem = t - ch * NB * R, dy = rem / R, cx = rem - dy * R;
         const float *p = prod + ch * R * R + dy * R + cx;
@@ -444,20 +464,16 @@ __device__ __forceinline__ void exact_values(const uint8_t *__restrict__ img, in
         col[t] = acc;
     }
     __syncwarp();
-    float v = FA_NEG_INF;
-    if (lane < NB * NB) {
-        const int dy = lane / NB, dx = lane - dy * NB;
-        double sums[3];
+    double sum = 0.0;                                            // lane = channel * NB^2 + window
+    if (lane < 3 * NB * NB) {
+        const int ch = lane / (NB * NB), wnd = lane - ch * NB * NB, dy = wnd / NB, dx = wnd - dy * NB;
+        const double *c = col + (ch * NB + dy) * R + dx;
 #pragma unroll
-        for (int ch = 0; ch < 3; ch++) {
-            const double *c = col + (ch * NB + dy) * R + dx;
-            double acc = 0.0;
-#pragma unroll
-            for (int k = 0; k < 15; k++) acc += c[k];
-            sums[ch] = acc;
-        }
-        v = eig_from_sums(sums[0], sums[1], sums[2]);
+        for (int k = 0; k < 15; k++) sum += c[k];
     }
+    const double sxy = shfl_f64(sum, lane + NB * NB), syy = shfl_f64(sum, lane + 2 * NB * NB);
+    float v = FA_NEG_INF;
+    if (lane < NB * NB) v = eig_from_sums(sum, sxy, syy);
     v_centre = __shfl_sync(0xffffffffu, v, (NB * NB) / 2);
     float mx = v;
     for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));

@@ -224,6 +224,25 @@ def mi_golden():
           int(np.isnan(out["svc_studholme_f32"]).sum()))
 
 
+def scene_golden():
+    """shift_image (karios/core/image.py:70-101) through the unmodified reference, for
+    the offset signs / magnitudes of its four branches and the rounding of float offsets."""
+    im = refimport.load_core_image()
+    rng = np.random.default_rng(9)
+    a16 = rng.integers(1, 60000, (37, 53)).astype(np.uint16)
+    a8 = rng.integers(1, 255, (20, 31)).astype(np.uint8)
+    af = rng.random((16, 18)).astype(np.float32)
+    out = dict(a16=a16, a8=a8, af=af)
+    offs = [(0, 0), (3, 0), (0, -4), (-5, 7), (6, -2), (2.5, -3.5), (1.4999, 0.5), (-36, 52), (40, 0)]
+    out["offsets"] = np.array(offs, np.float64)
+    for k, (yo, xo) in enumerate(offs):
+        out[f"s16_{k}"] = im.shift_image(a16, y_off=yo, x_off=xo)
+        out[f"s8_{k}"] = im.shift_image(a8, y_off=yo, x_off=xo)
+        out[f"sf_{k}"] = im.shift_image(af, y_off=yo, x_off=xo)
+    np.savez_compressed(os.path.join(OUT, "scene_ops.npz"), **out)
+    print("scene_ops", len(offs), "offsets")
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     cv2.setNumThreads(1)
@@ -240,3 +259,4 @@ if __name__ == "__main__":
               blocksize=7, maxCorners=2000), negate_mon=True)
     zncc_known_answers()
     mi_golden()
+    scene_golden()

@@ -459,3 +459,70 @@ def mutual_info(x0, y0, dx, dy, monitored: np.ndarray, reference: np.ndarray):
         except Exception:  # noqa: BLE001 - zncc_service.py:283-287
             pass
     return st, mi
+
+
+# --------------------------------------------------------------------------- f2
+def phase_cross_correlation_shift(reference_image, moving_image):
+    """Whole-pixel part of skimage.registration.phase_cross_correlation(reference,
+    moving) as LargeOffsetMatcher.match uses it (karios/matcher/large_offset.py:32-41,
+    called with (mon, ref)).  scikit-image is pinned by the reference
+    (environment.yml: scikit-image=0.24.*) but is not installed here nor vendored
+    under /root/reference: this restates the published algorithm of
+    skimage/registration/_phase_cross_correlation.py (0.24) for upsample_factor = 1,
+    space = "real", normalization = "phase".  PARITY UNPINNED by reference vectors
+    (the reference's tests mock this call, tests/test_large_offset_matcher.py:26-48);
+    pinned by known-answer shifts in tests/test_oracle.py."""
+    src_freq = np.fft.fftn(np.asarray(reference_image, np.float64))
+    target_freq = np.fft.fftn(np.asarray(moving_image, np.float64))
+    shape = src_freq.shape
+    image_product = src_freq * target_freq.conj()
+    eps = np.finfo(image_product.real.dtype).eps
+    image_product /= np.maximum(np.abs(image_product), 100 * eps)
+    cross_correlation = np.fft.ifftn(image_product)
+    maxima = np.unravel_index(np.argmax(np.abs(cross_correlation)), cross_correlation.shape)
+    midpoint = np.array([np.fix(axis_size / 2) for axis_size in shape])
+    shift = np.stack(maxima).astype(np.float64, copy=False)
+    shift[shift > midpoint] -= np.array(shape)[shift > midpoint]
+    for dim in range(src_freq.ndim):
+        if shape[dim] == 1:
+            shift[dim] = 0
+    return shift
+
+
+def shift_image(img, y_off=0, x_off=0):
+    """shift_image (karios/core/image.py:70-101)."""
+    y_off, x_off = int(round(y_off)), int(round(x_off))
+    h, w = img.shape
+    out = np.zeros(img.shape, img.dtype)
+    ys, xs = np.arange(h) + y_off, np.arange(w) + x_off
+    yv, xv = (ys >= 0) & (ys < h), (xs >= 0) & (xs < w)
+    out[np.ix_(yv, xv)] = img[np.ix_(ys[yv], xs[xv])]
+    return out
+
+
+# --------------------------------------------------------------------------- f3
+def percentiles_2_98(arr):
+    """_check_quality (karios/api/core.py:500-506)."""
+    return np.nanpercentile(arr, [2, 98])
+
+
+def count_valid_pixels(mon, mask=None):
+    """analyze_accuracy (karios/api/core.py:285-290)."""
+    masked = mon
+    if mask is not None:
+        masked = np.copy(mon)
+        masked[mask == 0] = 0
+    return int(np.count_nonzero(masked))
+
+
+def filter_by_dn_values(x0, y0, mon, ref, no_values=None, mon_nd=None, ref_nd=None):
+    """_filter_by_dn_values (karios/api/core.py:687-728) -> boolean keep mask."""
+    xi, yi = np.asarray(x0).astype(int), np.asarray(y0).astype(int)
+    rv, mv = ref[yi, xi], mon[yi, xi]
+    keep = np.ones(len(xi), dtype=bool)
+    for nv in no_values or []:
+        keep &= ~((rv == nv) | (mv == nv))
+    for nd, vals in ((ref_nd, rv), (mon_nd, mv)):
+        if nd is not None:
+            keep &= ~(vals == nd)
+    return keep

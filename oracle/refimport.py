@@ -52,6 +52,12 @@ def load_mutual_info():
     return importlib.import_module("karios.matcher.mutual_info_service")
 
 
+def load_core_image():
+    """-> the unmodified karios/core/image.py module (shift_image)."""
+    load()
+    return importlib.import_module("karios.core.image")
+
+
 class ArrayImage:
     """Duck-typed stand-in for GdalRasterImage (karios/core/image.py:255) over an
     in-memory array: .read/.array/.x_size/.y_size/.no_data_value/.clear_cache."""

@@ -416,6 +416,102 @@ def test_mutual_info_fused_in_match_tile(N):
     assert (~np.isnan(got[0])).sum() > 50
 
 
+def test_large_offset_matcher():
+    """LargeOffsetMatcher.match (whole-pixel phase correlation) against the NumPy
+    restatement of skimage's algorithm: circular shifts, a zero-filled large shift of a
+    uint16 scene (BASELINE config 4), odd sizes."""
+    from karios_b200.core.image import ArrayRaster, DeviceRaster
+    from karios_b200.matcher.large_offset import LargeOffsetMatcher, phase_cross_correlation_shift
+    rng = np.random.default_rng(2)
+    base = rng.random((96, 120))
+    for dy, dx in ((0, 0), (3, -5), (-20, 11), (47, 59), (-48, -60)):
+        moving = np.roll(base, (dy, dx), axis=(0, 1))
+        got = phase_cross_correlation_shift(base, moving)
+        assert got.dtype == np.float64 and np.array_equal(got, O.phase_cross_correlation_shift(base, moving))
+    # uint16 scene displaced by whole pixels with zero fill (BASELINE config 4 geometry)
+    ref = (rng.random((601, 777)) * 3000 + 1000).astype(np.uint16)
+    mon = O.shift_image(ref, y_off=52, x_off=-37)
+    want = O.phase_cross_correlation_shift(mon, ref)
+    got = LargeOffsetMatcher(ArrayRaster(ref), ArrayRaster(mon)).match()
+    assert np.array_equal(got, want) and np.array_equal(want, [-52, 37]), (got, want)
+    got = LargeOffsetMatcher(DeviceRaster(dev(ref.view(np.int16)).view(torch.uint16)),
+                             DeviceRaster(dev(mon.view(np.int16)).view(torch.uint16))).match()
+    assert np.array_equal(got, want)
+
+
+def test_shift_image(golden):
+    from karios_b200.core.image import shift_image
+    g = golden("scene_ops")
+    for k, (yo, xo) in enumerate(g["offsets"]):
+        for src, key in ((g["a16"], "s16"), (g["a8"], "s8"), (g["af"], "sf")):
+            got = shift_image(src, y_off=yo, x_off=xo)
+            assert got.dtype == src.dtype and np.array_equal(got, g[f"{key}_{k}"]), (k, key)
+    t = shift_image(dev(g["a16"].view(np.int16)), y_off=-5, x_off=7)
+    assert t.is_cuda and np.array_equal(t.cpu().numpy().view(np.uint16), g["s16_3"])
+
+
+def test_scene_scans():
+    """_check_quality percentiles, valid-pixel count, DN filter and DEM lookup
+    (karios/api/core.py:500-506, 285-290, 687-728, 1050-1053) against NumPy."""
+    import pandas as pd
+    from karios_b200 import api
+    from karios_b200.core.image import ArrayRaster
+    rng = np.random.default_rng(6)
+    for shape, lo, hi, dt in (((300, 411), 900, 4100, np.uint16), ((257, 300), 0, 65535, np.uint16),
+                              ((200, 200), 0, 255, np.uint8), ((123, 321), -2000, 2500, np.int16),
+                              ((64, 64), 1200, 1204, np.uint16)):
+        a = rng.integers(lo, hi + 1, shape).astype(dt)
+        got = api.percentiles_2_98(ArrayRaster(a))
+        assert np.array_equal(got, O.percentiles_2_98(a)), (shape, got, O.percentiles_2_98(a))
+    skew = (rng.gamma(2.0, 300.0, (500, 300))).astype(np.uint16)
+    assert np.array_equal(api.percentiles_2_98(ArrayRaster(skew)), O.percentiles_2_98(skew))
+    q = api.check_quality(ArrayRaster(np.full((50, 50), 7, np.uint16)), ArrayRaster(skew))
+    assert q["monitored"]["low_dynamic"] and not q["reference"]["low_dynamic"]
+    mon = rng.integers(0, 5, (140, 150)).astype(np.uint16)
+    ref = rng.integers(0, 5, (140, 150)).astype(np.uint16)
+    mask = (rng.random((140, 150)) > 0.4).astype(np.uint8)
+    assert api.count_valid_pixels(ArrayRaster(mon)) == O.count_valid_pixels(mon)
+    assert api.count_valid_pixels(ArrayRaster(mon), ArrayRaster(mask)) == O.count_valid_pixels(mon, mask)
+    x0 = rng.uniform(0, 149.9, 500).astype(np.float32)
+    y0 = rng.uniform(0, 139.9, 500).astype(np.float32)
+    df = pd.DataFrame({"x0": x0, "y0": y0, "dx": 0.0, "dy": 0.0})
+    out = api.filter_by_dn_values(df, ArrayRaster(mon, no_data_value=3), ArrayRaster(ref), no_values=[0])
+    keep = O.filter_by_dn_values(x0, y0, mon, ref, no_values=[0], mon_nd=3)
+    assert out.index.equals(df.index[keep]) and 0 < len(out) < 500
+    dem = (rng.random((140, 150)) * 3000).astype(np.float32)
+    alt = api.dem_altitudes(df, ArrayRaster(dem))
+    assert alt.dtype == np.float32 and np.array_equal(alt, dem[y0.astype(int), x0.astype(int)])
+    centres, cnt, mean, std = api.altitude_profile(x0, alt, 100)
+    grp = pd.DataFrame({"val": x0.astype(np.float64), "po": np.floor_divide(alt, 100)}).groupby("po")["val"]
+    assert np.array_equal(cnt, grp.count().to_numpy()) and np.allclose(mean, grp.mean().to_numpy(), rtol=1e-12)
+    assert np.allclose(std, grp.std().to_numpy(), rtol=1e-9, equal_nan=True)
+
+
+def test_large_shift_flow():
+    """BASELINE config 4: monitored raster displaced by (+37 columns, -52 rows); the
+    detected offset is undone, KLT runs on the shifted raster, dx / dy get the offset
+    back (karios/api/core.py:233-252) -- against the oracle run on the same steps."""
+    from karios_b200 import api, synth
+    from karios_b200.core.configuration import KLTConfiguration
+    ref_t, _ = synth.make_pair(500, 640, seed=12)
+    to_np = lambda t: t.view(torch.int16).numpy().view(np.uint16)  # noqa: E731
+    rng = np.random.default_rng(12)
+    ref = (to_np(ref_t).astype(np.int32) + rng.integers(-60, 61, (500, 640))).astype(np.uint16)
+    mon = O.shift_image(ref, y_off=52, x_off=-37)               # content moves by (+37, -52)
+    conf = KLTConfiguration(maxCorners=800)
+    df, applied = api.match_pair_large_shift(mon, ref, None, conf, offset_threshold=15)
+    off = O.phase_cross_correlation_shift(mon, ref)
+    assert np.array_equal(off, [-52, 37]) and applied == (37.0, -52.0)
+    shifted = O.shift_image(mon, y_off=off[0], x_off=off[1])
+    want = O.match(shifted, ref, None, O.KLTConfiguration(maxCorners=800))[0]
+    assert np.array_equal(df["x0"].to_numpy(), want["x0"]) and np.array_equal(df["y0"].to_numpy(), want["y0"])
+    assert np.abs(df["dx"].to_numpy() - (want["dx"] + off[1])).max() < 1e-3
+    assert np.abs(df["dy"].to_numpy() - (want["dy"] + off[0])).max() < 1e-3
+    assert np.isnan(df["zncc_score"]).all() and len(df) > 300
+    small, none = api.match_pair_large_shift(ref, ref, None, conf, offset_threshold=15)
+    assert none is None and len(small) > 300 and not np.isnan(small["zncc_score"]).all()
+
+
 def test_sort_and_unlimited_corners(N):
     """maxCorners = 0 exercises the multi-chunk sort and the full NMS."""
     from karios_b200 import synth

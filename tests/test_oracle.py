@@ -227,3 +227,43 @@ def test_integer_joint_histogram_equals_numpy():
     a = rng.integers(-3000, 3000, (57, 57)).astype(np.int16)
     b = rng.integers(-32768, 32767, (57, 57)).astype(np.int16)
     assert np.array_equal(O.joint_histogram_int(a, b), np.histogram2d(a.ravel(), b.ravel(), bins=32)[0])
+
+
+# ------------------------------------------------------------------ f2 / f3: scene-level passes
+def test_shift_image_matches_reference(golden):
+    g = golden("scene_ops")
+    for k, (yo, xo) in enumerate(g["offsets"]):
+        for src, key in ((g["a16"], "s16"), (g["a8"], "s8"), (g["af"], "sf")):
+            assert np.array_equal(O.shift_image(src, y_off=yo, x_off=xo), g[f"{key}_{k}"]), (k, key)
+
+
+def test_phase_correlation_known_shifts():
+    """skimage is absent (parity unpinned by reference vectors): the restatement must
+    recover circular and zero-filled whole-pixel shifts, with skimage's sign."""
+    rng = np.random.default_rng(2)
+    base = rng.random((96, 120))
+    for dy, dx in ((0, 0), (3, -5), (-20, 11), (47, 59), (-48, -60)):
+        moving = np.roll(base, (dy, dx), axis=(0, 1))
+        assert np.array_equal(O.phase_cross_correlation_shift(base, moving), [-dy, -dx]), (dy, dx)
+    ref = (rng.random((160, 200)) * 3000 + 1000).astype(np.uint16)
+    mon = O.shift_image(ref, y_off=-13, x_off=21)              # config 4 style: zero fill
+    # LargeOffsetMatcher calls (mon, ref); shifting mon by the result re-aligns it
+    off = O.phase_cross_correlation_shift(mon, ref)
+    back = O.shift_image(mon, y_off=off[0], x_off=off[1])
+    inner = (slice(30, 130), slice(30, 170))
+    assert np.array_equal(back[inner], ref[inner])
+
+
+def test_filter_and_count_restatements():
+    rng = np.random.default_rng(4)
+    mon = rng.integers(0, 5, (40, 50)).astype(np.uint16)
+    ref = rng.integers(0, 5, (40, 50)).astype(np.uint16)
+    mask = (rng.random((40, 50)) > 0.4).astype(np.uint8)
+    assert O.count_valid_pixels(mon) == int((mon != 0).sum())
+    assert O.count_valid_pixels(mon, mask) == int(((mon != 0) & (mask != 0)).sum())
+    x0 = rng.uniform(0, 49.9, 200).astype(np.float32)
+    y0 = rng.uniform(0, 39.9, 200).astype(np.float32)
+    keep = O.filter_by_dn_values(x0, y0, mon, ref, no_values=[0], mon_nd=3)
+    xi, yi = x0.astype(int), y0.astype(int)
+    want = (mon[yi, xi] != 0) & (ref[yi, xi] != 0) & (mon[yi, xi] != 3)
+    assert np.array_equal(keep, want) and 0 < keep.sum() < 200
