@@ -280,8 +280,16 @@ def cuda_arm(args):
                   "gbs": round(sb[k] / (acc[k] * 1e6), 1) if acc[k] > 0 else None} for k in acc}
     dom = max(acc, key=lambda k: acc[k])
     achieved = sb[dom] / (acc[dom] * 1e6) if acc[dom] > 0 else 0.0
+    traffic, traffic_src = None, None
+    try:        # dram__bytes_read + write of the stage's kernels, one ncu --set full capture (profiles/)
+        tj = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+        if size == S2 and dom in tj["stages"]:
+            traffic, traffic_src = tj["stages"][dom]["dram_bytes"], tj["source"]
+    except Exception:  # noqa: BLE001
+        pass
     roofline = {"bound": "hbm", "kernel": dom, "achieved": round(achieved, 1), "peak": hbm_peak,
-                "unit": "GB/s", "frac": round(achieved / hbm_peak, 4), "traffic": None,
+                "unit": "GB/s", "frac": round(achieved / hbm_peak, 4), "traffic": traffic,
+                "traffic_source": traffic_src,
                 "peak_source": peak_src, "kernel_ms": round(acc[dom], 4),
                 "alg_bytes_per_launch": sb[dom]}
     total_alg = sum(sb.values())
@@ -313,6 +321,43 @@ def cuda_arm(args):
             "bound": "shared-memory atomics + L1/L2 gathers (chips are re-read from cache)"}
     except Exception as e:  # noqa: BLE001
         next_rows["mutual_info"] = {"error": repr(e)}
+    try:
+        from karios_b200 import api as kapi
+        from karios_b200.core.image import DeviceRaster
+        from karios_b200.matcher.large_offset import phase_cross_correlation_shift
+        mon, ref = scenes[0]
+
+        def timed(fn, reps_=3):
+            fn()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            a.record()
+            for _ in range(reps_):
+                out = fn()
+            b.record()
+            torch.cuda.synchronize()
+            return a.elapsed_time(b) / reps_, out
+
+        ms_lo, off = timed(lambda: phase_cross_correlation_shift(mon, ref), 2)
+        # algorithmic traffic of the three float64 transforms is library-internal; the two
+        # own kernels stream the half spectrum twice and the correlation once
+        spec_bytes = size * (size // 2 + 1) * 16
+        next_rows["large_offset"] = {
+            "what": "LargeOffsetMatcher.match: 2 rfft2 + cross-power + irfft2 + argmax, float64 (cuFFT + 2 own kernels)",
+            "ms": round(ms_lo, 3), "offset_yx": [float(off[0]), float(off[1])],
+            "own_kernel_alg_bytes": 3 * spec_bytes + P * 8, "bound": "cuFFT (library) dominates"}
+        ms_sh, _ = timed(lambda: N.shift_image(mon, 52, -37))
+        next_rows["shift_image"] = {"ms": round(ms_sh, 4), "alg_bytes": 2 * P * 2,
+                                    "gbs": round(2 * P * 2 / (ms_sh * 1e6), 1), "bound": "hbm"}
+        ms_pc, pct = timed(lambda: kapi.percentiles_2_98(DeviceRaster(mon)))
+        next_rows["percentiles_2_98"] = {"ms": round(ms_pc, 3), "value": [float(pct[0]), float(pct[1])],
+                                         "alg_bytes": 8 * P * 2, "gbs": round(8 * P * 2 / (ms_pc * 1e6), 1),
+                                         "bound": "L2 / shared-memory atomics (8 range passes over the raster)"}
+        ms_cv, nvalid = timed(lambda: kapi.count_valid_pixels(DeviceRaster(mon)))
+        next_rows["count_valid"] = {"ms": round(ms_cv, 4), "value": int(nvalid), "alg_bytes": P * 2,
+                                    "gbs": round(P * 2 / (ms_cv * 1e6), 1), "bound": "hbm"}
+    except Exception as e:  # noqa: BLE001
+        next_rows["scene_passes"] = {"error": repr(e)}
 
     # ---- end to end: pinned host rasters -> rows on the host -----------------
     e2e = None
@@ -357,6 +402,17 @@ def cuda_arm(args):
             dt_mi = time.perf_counter() - t0
             next_rows["mutual_info"]["cpu_rows_per_sec"] = round(k / dt_mi, 1)
             next_rows["mutual_info"]["cpu_sample"] = f"{k} rows, oracle.mutual_info (np.histogram2d per row, 1 core)"
+        if "ms" in next_rows.get("large_offset", {}):
+            side = min(size, 2048)
+            t0 = time.perf_counter()
+            O.phase_cross_correlation_shift(mon_h[:side, :side], ref_h[:side, :side])
+            dt_lo = time.perf_counter() - t0
+            next_rows["large_offset"]["cpu_seconds_sample"] = round(dt_lo, 3)
+            next_rows["large_offset"]["cpu_sample"] = (f"{side}x{side} crop, oracle (numpy.fft float64, 1 core); "
+                                                       f"the full frame is {(size / side) ** 2:.0f}x the pixels")
+            t0 = time.perf_counter()
+            O.percentiles_2_98(mon_h)
+            next_rows["percentiles_2_98"]["cpu_seconds"] = round(time.perf_counter() - t0, 3)
 
     if rank == 0:
         line = {
@@ -380,7 +436,7 @@ def cuda_arm(args):
             "cpu_baseline": cpu,
             "e2e": e2e,
             "next_rows": next_rows,
-            "gpu_launches": 23 * args.steps * len(sm.windows),
+            "gpu_launches": 28 * args.steps * len(sm.windows),      # own kernels per tile (profiles/ncu_launches_*.csv)
             "clocks": sampler.summary(),
             "stats_last": {k: v for k, v in st.as_dict().items() if k.startswith("n_") or k == "nms_rounds"},
         }

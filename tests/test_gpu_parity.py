@@ -599,6 +599,59 @@ def test_full_s2_scene_properties_and_opencv():
                   open(os.path.join(out, "full_scene_parity.json"), "w"))
 
 
+def test_full_s2_mask_tiles_dem_vs_opencv():
+    """BASELINE configs 2 ("full tiling", tile_size 6000 -> 4 tiles) and 3 (user mask
+    zeroing ~30 % of the scene, DEM altitudes): a 10980 x 10980 pair through
+    SceneMatcher.match_many with two pairs' worth of tiles in flight, against the
+    reference's OpenCV calls on the same arrays (oracle/cv2_path.py)."""
+    from karios_b200 import api, synth
+    from karios_b200.api import SceneMatcher
+    from karios_b200.core.configuration import KLTConfiguration
+    from karios_b200.core.image import DeviceRaster
+    from oracle import cv2_path as P
+    if not P.HAVE_CV2:
+        pytest.skip("cv2 not importable here")
+    size = 10980
+    ref_t, mon_t = synth.make_pair(size, size, seed=1235, device="cuda")
+    mask_t = synth.make_mask(size, size, seed=99, device="cuda")
+    conf = KLTConfiguration(tile_size=6000)
+    sm = SceneMatcher(size, size, conf, 0.4, depth=2)
+    try:
+        assert len(sm.windows) == 4
+        res, total = sm.match_many([(mon_t, ref_t)], mask=mask_t)
+        df = sm.to_frame(res[0])
+    finally:
+        sm.close()
+    to_np = lambda t: t.cpu().view(torch.int16).numpy().view(np.uint16)  # noqa: E731
+    ref, mon, mask = to_np(ref_t), to_np(mon_t), mask_t.cpu().numpy()
+    tiles_cv, total_cv = P.match_scene(mon, ref, mask, O.KLTConfiguration(tile_size=6000))
+    assert len(tiles_cv) == 4 and len(res[0]) == 4
+    n_id, n_all, worst, zworst = 0, 0, 0.0, 0.0
+    for (f, z), c in zip(res[0], tiles_cv):              # tile order: x outer, y inner
+        f = f.cpu().numpy()
+        z = z.cpu().numpy()
+        key = f[0].astype(np.int64) * 65536 + f[1].astype(np.int64)
+        key_cv = c["x0"].astype(np.int64) * 65536 + c["y0"].astype(np.int64)
+        assert (np.diff(key) > 0).all()
+        common, ia, ib = np.intersect1d(key, key_cv, return_indices=True)
+        n_id += len(common)
+        n_all += max(len(key), len(key_cv))
+        worst = max(worst, np.abs(f[2][ia] - c["dx"][ib]).max(), np.abs(f[3][ia] - c["dy"][ib]).max())
+        assert np.array_equal(np.isnan(z[ia]), np.isnan(c["zncc"][ib]))
+        zworst = max(zworst, np.nanmax(np.abs(z[ia] - c["zncc"][ib])))
+        m = mask[f[1].astype(int), f[0].astype(int)]
+        assert (m != 0).all()                             # no corner in a masked-out pixel
+    print(f"tiles+mask: common {n_id}/{n_all}, max |d| {worst:.2e}, zncc {zworst:.2e}")
+    assert n_id / n_all >= 0.999 and worst < 1e-3 and zworst < 1e-5
+    # config 3: DEM altitudes of the key points and valid-pixel count under the mask
+    dem_t = (torch.arange(size, device="cuda", dtype=torch.float32)[:, None] * 0.2 +
+             torch.arange(size, device="cuda", dtype=torch.float32)[None, :] * 0.07)
+    alt = api.dem_altitudes(df, DeviceRaster(dem_t))
+    want = dem_t.cpu().numpy()[df["y0"].to_numpy().astype(int), df["x0"].to_numpy().astype(int)]
+    assert np.array_equal(alt, want)
+    assert api.count_valid_pixels(DeviceRaster(mon_t), DeviceRaster(mask_t)) == O.count_valid_pixels(mon, mask)
+
+
 def test_smoke_entry():
     import __graft_entry__ as ge
     ge.smoke()
