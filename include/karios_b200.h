@@ -233,11 +233,12 @@ KR_API int kr_argmax_abs(const void *x, int64_t n, int is_double, void *scratch1
 KR_API int kr_shift_image(const void *src, int64_t src_pitch, void *dst, int64_t dst_pitch, int dtype,
                           int w, int h, int x_off, int y_off, void *stream);
 
-/* Value histogram of an integer raster over [lo, lo + nbins), nbins <= 8192 per call,
- * ADDED to hist[nbins] (device uint64): np.nanpercentile(image, [2, 98]) of
- * KariosAPI._check_quality (karios/api/core.py:500-506) is read off it. */
-KR_API int kr_histogram(const void *img, int64_t pitch, int dtype, int w, int h, int lo, int nbins,
-                        uint64_t *hist, void *stream);
+/* Histogram of an integer raster: bin = (value - lo) >> shift for value >= lo and
+ * bin < nbins (<= 8192 per call), ADDED to hist[nbins] (device uint64).
+ * np.nanpercentile(image, [2, 98]) of KariosAPI._check_quality
+ * (karios/api/core.py:500-506) is read off a coarse pass and a refinement. */
+KR_API int kr_histogram(const void *img, int64_t pitch, int dtype, int w, int h, int lo, int shift,
+                        int nbins, uint64_t *hist, void *stream);
 
 /* np.count_nonzero(image) with image[mask == 0] = 0 when a mask is given
  * (karios/api/core.py:285-290) -> *d_count (device uint64). */

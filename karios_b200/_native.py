@@ -112,7 +112,7 @@ def load_library(path: str = LIB_PATH):
         L.kr_cross_power.argtypes = [vp, vp, i64, i32, vp]
         L.kr_argmax_abs.argtypes = [vp, i64, i32, vp, vp, vp]
         L.kr_shift_image.argtypes = [vp, i64, vp, i64, i32, i32, i32, i32, i32, vp]
-        L.kr_histogram.argtypes = [vp, i64, i32, i32, i32, i32, i32, vp, vp]
+        L.kr_histogram.argtypes = [vp, i64, i32, i32, i32, i32, i32, i32, vp, vp]
         L.kr_count_valid.argtypes = [vp, i64, i32, i32, i32, vp, i64, vp, vp]
         L.kr_gather_points.argtypes = [vp, i64, i32, i32, i32, vp, vp, i32, vp, vp]
         for name in EXPORTS:
@@ -460,16 +460,18 @@ def shift_image(img: torch.Tensor, y_off=0, x_off=0) -> torch.Tensor:
     return out
 
 
-def histogram(img: torch.Tensor, lo: int, hi: int) -> torch.Tensor:
-    """Counts of the integer values lo..hi (inclusive) -> device int64 tensor [hi - lo + 1]."""
+def histogram(img: torch.Tensor, lo: int, hi: int, shift: int = 0) -> torch.Tensor:
+    """Counts of (value - lo) >> shift for the integer values lo..hi (inclusive)
+    -> device int64 tensor [((hi - lo) >> shift) + 1]."""
     lib = _require_cuda()
     h, w = img.shape
-    n = int(hi) - int(lo) + 1
+    n = ((int(hi) - int(lo)) >> shift) + 1
     hist = torch.zeros(n, dtype=torch.int64, device=img.device)
     for start in range(0, n, 8192):
         nb = min(8192, n - start)
-        _check(lib.kr_histogram(img.data_ptr(), _pitch(img), dtype_code(img), w, h, int(lo) + start, nb,
-                                hist[start:].data_ptr(), _stream()))
+        _check(lib.kr_histogram(img.data_ptr(), _pitch(img), dtype_code(img), w, h,
+                                int(lo) + (start << shift), int(shift), nb, hist[start:].data_ptr(),
+                                _stream()))
     return hist
 
 

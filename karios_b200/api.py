@@ -240,9 +240,24 @@ def percentiles_2_98(raster) -> np.ndarray:
     info = {torch.uint8: (0, 255), torch.uint16: (0, 65535), torch.int16: (-32768, 32767)}
     if t.dtype not in info:
         raise N.KariosB200Error("percentiles need an integer raster (uint8, uint16, int16)")
-    lo, hi = info[t.dtype]                           # full value range: 8 passes of 8192 bins for 16 bits
-    cum = torch.cumsum(N.histogram(t, lo, hi), 0).cpu().numpy()
-    n = int(cum[-1])
+    lo, hi = info[t.dtype]
+    # coarse pass over the whole value range (8 values per bin for 16 bits), then the
+    # few coarse bins that hold the wanted order statistics at full resolution
+    shift = 0 if t.dtype == torch.uint8 else 3
+    coarse = torch.cumsum(N.histogram(t, lo, hi, shift), 0).cpu().numpy()
+    n = int(coarse[-1])
+    fine = {}
+
+    def value_at(k):                                   # k-th smallest value (0-based)
+        cb = int(np.searchsorted(coarse, k + 1, side="left"))
+        if shift == 0:
+            return lo + cb
+        if cb not in fine:
+            fine[cb] = torch.cumsum(N.histogram(t, lo + (cb << shift), lo + (cb << shift) + (1 << shift) - 1),
+                                    0).cpu().numpy()
+        below = int(coarse[cb - 1]) if cb > 0 else 0
+        return lo + (cb << shift) + int(np.searchsorted(fine[cb], k + 1 - below, side="left"))
+
     out = []
     for q in (np.float64(2) / 100, np.float64(98) / 100):
         virtual = n * q + (1 + q * (1 - 1 - 1)) - 1          # numpy _compute_virtual_index, alpha = beta = 1
@@ -250,8 +265,7 @@ def percentiles_2_98(raster) -> np.ndarray:
         gamma = virtual - prev
         k0 = int(prev)
         k1 = min(k0 + 1, n - 1)
-        a = np.float64(lo + int(np.searchsorted(cum, k0 + 1, side="left")))
-        b = np.float64(lo + int(np.searchsorted(cum, k1 + 1, side="left")))
+        a, b = np.float64(value_at(k0)), np.float64(value_at(k1))
         diff = b - a
         out.append(a + diff * gamma if gamma < 0.5 else b - diff * (1 - gamma))   # numpy _lerp
     return np.array(out)

@@ -107,7 +107,7 @@ constexpr int HIST_SPAN = 8192;                    // bins per pass (32 KB of sh
 
 template <typename T>
 __global__ void __launch_bounds__(256)
-k_histogram(const T *__restrict__ img, int64_t pitch, int w, int h, int lo, int nbins,
+k_histogram(const T *__restrict__ img, int64_t pitch, int w, int h, int lo, int shift, int nbins,
             unsigned long long *__restrict__ hist)
 {
     __shared__ uint32_t sh[HIST_SPAN];
@@ -116,8 +116,9 @@ k_histogram(const T *__restrict__ img, int64_t pitch, int w, int h, int lo, int 
     for (int y = blockIdx.x; y < h; y += gridDim.x) {
         const T *row = (const T *)((const char *)img + (int64_t)y * pitch);
         for (int x = threadIdx.x; x < w; x += blockDim.x) {
-            const int b = (int)row[x] - lo;
-            if (b >= 0 && b < nbins) atomicAdd(&sh[b], 1u);
+            const int d = (int)row[x] - lo;
+            const int b = d >> shift;
+            if (d >= 0 && b < nbins) atomicAdd(&sh[b], 1u);
         }
     }
     __syncthreads();
@@ -210,18 +211,18 @@ KR_API int kr_shift_image(const void *src, int64_t src_pitch, void *dst, int64_t
     return KR_OK;
 }
 
-KR_API int kr_histogram(const void *img, int64_t pitch, int dtype, int w, int h, int lo, int nbins,
-                        uint64_t *hist, void *stream)
+KR_API int kr_histogram(const void *img, int64_t pitch, int dtype, int w, int h, int lo, int shift,
+                        int nbins, uint64_t *hist, void *stream)
 {
-    if (!img || !hist || w < 1 || h < 1 || nbins < 1 || nbins > HIST_SPAN)
+    if (!img || !hist || w < 1 || h < 1 || nbins < 1 || nbins > HIST_SPAN || shift < 0 || shift > 16)
         return kr_set_error(KR_ERR_INVALID, "bad histogram arguments (1..%d bins per pass)", HIST_SPAN);
     cudaStream_t s = (cudaStream_t)stream;
     const int grid = h < 148 * 4 ? h : 148 * 4;
     unsigned long long *hh = (unsigned long long *)hist;
     switch (dtype) {
-    case KR_U8: k_histogram<uint8_t><<<grid, 256, 0, s>>>((const uint8_t *)img, pitch, w, h, lo, nbins, hh); break;
-    case KR_U16: k_histogram<uint16_t><<<grid, 256, 0, s>>>((const uint16_t *)img, pitch, w, h, lo, nbins, hh); break;
-    case KR_I16: k_histogram<int16_t><<<grid, 256, 0, s>>>((const int16_t *)img, pitch, w, h, lo, nbins, hh); break;
+    case KR_U8: k_histogram<uint8_t><<<grid, 256, 0, s>>>((const uint8_t *)img, pitch, w, h, lo, shift, nbins, hh); break;
+    case KR_U16: k_histogram<uint16_t><<<grid, 256, 0, s>>>((const uint16_t *)img, pitch, w, h, lo, shift, nbins, hh); break;
+    case KR_I16: k_histogram<int16_t><<<grid, 256, 0, s>>>((const int16_t *)img, pitch, w, h, lo, shift, nbins, hh); break;
     default: return kr_set_error(KR_ERR_UNSUPPORTED, "histogram needs an integer raster (dtype %d)", dtype);
     }
     KR_LAUNCH_CHECK();

@@ -39,17 +39,15 @@ def gather_matches(unit_ids: Sequence[int], unit_rows: Sequence[torch.Tensor], n
         counts[u] = rows.shape[0]
     dist.all_reduce(counts, op=dist.ReduceOp.SUM, group=group)       # every unit has one owner
     per_rank = (n_units + world - 1) // world
-    n_max = int(counts.max().item()) if n_units else 0
+    cnt = counts.cpu().tolist()                                      # the one host synchronisation
+    n_max = max(cnt) if n_units else 0
     mine = torch.zeros((per_rank, max(n_max, 1), len(COLUMNS)), dtype=torch.float64, device=dev)
     for slot, (u, rows) in enumerate(zip(unit_ids, unit_rows)):
         mine[slot, : rows.shape[0]] = rows
-    allr = [torch.empty_like(mine) for _ in range(world)]
-    dist.all_gather(allr, mine, group=group)
-    out = []
-    for u in range(n_units):
-        r, slot = u % world, u // world
-        out.append(allr[r][slot, : int(counts[u])].clone())
-    return out
+    allr = torch.empty((world,) + tuple(mine.shape), dtype=torch.float64, device=dev)
+    dist.all_gather(list(allr.unbind(0)), mine, group=group)
+    # views into the gathered block: unit u lives at [u % world, u // world]
+    return [allr[u % world, u // world, : cnt[u]] for u in range(n_units)]
 
 
 def gather_moments(rows: torch.Tensor, group=None):
@@ -65,8 +63,11 @@ def gather_moments(rows: torch.Tensor, group=None):
     hi = torch.stack([dx.max() if len(dx) else torch.tensor(-inf, dtype=torch.float64, device=dev),
                       dy.max() if len(dy) else torch.tensor(-inf, dtype=torch.float64, device=dev)])
     dist.all_reduce(m, op=dist.ReduceOp.SUM, group=group)
-    dist.all_reduce(lo, op=dist.ReduceOp.MIN, group=group)
-    dist.all_reduce(hi, op=dist.ReduceOp.MAX, group=group)
+    ext = torch.cat([-lo, hi])                                       # min and max in one collective
+    dist.all_reduce(ext, op=dist.ReduceOp.MAX, group=group)
+    lo, hi = -ext[:2], ext[2:]
+    m = m.cpu()
+    lo, hi = lo.cpu(), hi.cpu()
     n = float(m[0])
     if n == 0:
         return {"n": 0}

@@ -599,6 +599,39 @@ def test_full_s2_scene_properties_and_opencv():
                   open(os.path.join(out, "full_scene_parity.json"), "w"))
 
 
+def test_match_many_equals_sequential():
+    """SceneMatcher.match_many (units of several pairs in flight on their own contexts /
+    streams) returns, pair by pair and tile by tile, exactly what match_device returns
+    for each pair on its own -- rows, ZNCC and both mutual-information scores."""
+    from karios_b200 import synth
+    from karios_b200.api import SceneMatcher
+    from karios_b200.core.configuration import KLTConfiguration
+    pairs = []
+    for seed in (3, 4, 5, 6, 7):
+        ref_t, mon_t = synth.make_pair(420, 610, seed=seed, device="cuda")
+        pairs.append((mon_t, ref_t))
+    conf = KLTConfiguration(maxCorners=400, tile_size=350)
+    seq = SceneMatcher(420, 610, conf, 0.4, depth=1, with_mi=True)
+    par = SceneMatcher(420, 610, conf, 0.4, depth=3, with_mi=True)
+    try:
+        assert len(par.windows) == 4
+        got, total = par.match_many(pairs)
+        want_total = 0
+        for (mon_t, ref_t), tiles in zip(pairs, got):
+            want, n = seq.match_device(mon_t, ref_t)
+            want_total += n
+            assert len(want) == len(tiles) == 4
+            for a, b in zip(tiles, want):
+                for x, y in zip(a, b):
+                    assert torch.equal(torch.nan_to_num(x, nan=-7.0), torch.nan_to_num(y, nan=-7.0))
+        assert total == want_total > 1000
+        df = par.to_frame(got[0])
+        assert list(df.columns) == ["x0", "y0", "dx", "dy", "score", "zncc_score", "mutual_info_score", "mi_score"]
+    finally:
+        seq.close()
+        par.close()
+
+
 def test_full_s2_mask_tiles_dem_vs_opencv():
     """BASELINE configs 2 ("full tiling", tile_size 6000 -> 4 tiles) and 3 (user mask
     zeroing ~30 % of the scene, DEM altitudes): a 10980 x 10980 pair through
