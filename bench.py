@@ -41,7 +41,12 @@ def parse():
                     help="scene pairs in flight per GPU (independent contexts + streams)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    return ap.parse_args()
+    ap.add_argument("--quick", action="store_true",
+                    help="tuning runs: resident throughput and stage times only (no e2e, CPU or next-row legs)")
+    a = ap.parse_args()
+    if a.quick:
+        a.no_e2e = a.no_cpu_baseline = True
+    return a
 
 
 def default_conf(cls, **kw):
@@ -305,6 +310,8 @@ def cuda_arm(args):
     # ---- SURVEY 8(f) rows built so far, timed on the rows of the last pair -----
     next_rows = {}
     try:
+        if args.quick:
+            raise RuntimeError("skipped (--quick)")
         mon, ref = scenes[0]
         cols = [sm.rows.f32[i, : st.n_kept].contiguous() for i in range(4)]
         for _ in range(2):
@@ -329,6 +336,8 @@ def cuda_arm(args):
     except Exception as e:  # noqa: BLE001
         next_rows["mutual_info"] = {"error": repr(e)}
     try:
+        if args.quick:
+            raise RuntimeError("skipped (--quick)")
         from karios_b200 import api as kapi
         from karios_b200.core.image import DeviceRaster
         from karios_b200.matcher.large_offset import phase_cross_correlation_shift

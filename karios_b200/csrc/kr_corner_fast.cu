@@ -34,6 +34,7 @@
 // one-tier kernel (kr_set_select_all), as it does for a short pre-selection.
 #include <limits.h>
 #include <math.h>
+#include <stdlib.h>
 #include "kr_internal.cuh"
 
 namespace {
@@ -364,8 +365,8 @@ __device__ __forceinline__ void approx_body(
     }
 }
 
-template <bool HAS_MASK>
-__global__ void __launch_bounds__(FA_WARPS * 32, FA_BLOCKS_PER_SM)
+template <bool HAS_MASK, int BPS>
+__global__ void __launch_bounds__(FA_WARPS * 32, BPS)
 k_eig_approx(const uint8_t *__restrict__ img, uint32_t pitch, const uint8_t *__restrict__ mask,
              uint32_t mpitch, int w, int h, uint64_t *__restrict__ cand, uint32_t cand_cap,
              uint64_t *__restrict__ maxlist, uint32_t maxlist_cap, KrDevStats *st, int seg, int aligned,
@@ -615,19 +616,33 @@ __global__ void k_commit_exact(KrDevStats *st)
 int krl_eig_fast(kr_ctx *ctx, const uint8_t *img, int64_t pitch, const uint8_t *mask, int64_t mask_pitch,
                  int w, int h, float scale, int tail_start, cudaStream_t s)
 {
-    const size_t smem = (size_t)FA_WARPS * (FA_RING_I4 * 16 + FA_CBUF * 8);
-    static bool set = false;
-    if (!set) {
-        KR_CUDA(cudaFuncSetAttribute(k_eig_approx<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        KR_CUDA(cudaFuncSetAttribute(k_eig_approx<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        set = true;
-    }
+    // resident blocks per SM: 4 (128 registers per thread) or 5 (96), KR_EIG_BPS selects;
+    // KR_EIG_SMEM_PAD adds unused shared memory per block (caps the residency, for tuning)
+    struct Cfg { int bps; size_t smem; cudaError_t err; };
+    static const Cfg cfg = [] {
+        Cfg c;
+        const char *e = getenv("KR_EIG_BPS");
+        c.bps = (e && atoi(e) == 5) ? 5 : FA_BLOCKS_PER_SM;
+        const char *p = getenv("KR_EIG_SMEM_PAD");
+        c.smem = (size_t)FA_WARPS * (FA_RING_I4 * 16 + FA_CBUF * 8) + (p ? (size_t)atoi(p) : 0);
+        c.err = cudaFuncSetAttribute(k_eig_approx<true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.smem);
+        if (c.err == cudaSuccess)
+            c.err = cudaFuncSetAttribute(k_eig_approx<false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.smem);
+        if (c.err == cudaSuccess)
+            c.err = cudaFuncSetAttribute(k_eig_approx<true, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.smem);
+        if (c.err == cudaSuccess)
+            c.err = cudaFuncSetAttribute(k_eig_approx<false, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.smem);
+        return c;
+    }();
+    KR_CUDA(cfg.err);
+    const int bps = cfg.bps;
+    const size_t smem = cfg.smem;
     int aligned = ((uintptr_t)img % 4 == 0) && (pitch % 4 == 0);
     if (mask) aligned = aligned && ((uintptr_t)mask % 4 == 0) && (mask_pitch % 4 == 0);
     // rows per warp: whole waves of co-resident blocks; each segment pays 18 warm-up rows
     const int sb = (w + FA_WARPS * FA_OUTW - 1) / (FA_WARPS * FA_OUTW);
     int best_seg = h, best_cost = INT_MAX;
-    const int slots = ctx->num_sms * FA_BLOCKS_PER_SM;
+    const int slots = ctx->num_sms * ((smem > 46 * 1024 && bps > 4) ? 4 : bps);
     const int w0 = (int)(((int64_t)sb * ((h + 255) / 256) + slots - 1) / slots);
     for (int waves = (w0 > 1 ? w0 - 1 : 1); waves <= w0 + 1; waves++) {
         int segs = waves * slots / sb;
@@ -643,16 +658,14 @@ int krl_eig_fast(kr_ctx *ctx, const uint8_t *img, int64_t pitch, const uint8_t *
     dim3 grid(sb, (h + seg - 1) / seg);
     // the context's own auto mask: all-valid is known on the device (K1's count)
     const unsigned long long *valid = (mask && mask == ctx->d_mask) ? &ctx->d_stats->valid : nullptr;
-    if (mask)
-        k_eig_approx<true><<<grid, FA_WARPS * 32, smem, s>>>(img, (uint32_t)pitch, mask, (uint32_t)mask_pitch,
-                                                            w, h, ctx->d_cand, (uint32_t)ctx->cand_cap,
-                                                            ctx->d_maxlist, (uint32_t)ctx->maxlist_cap,
-                                                            ctx->d_stats, seg, aligned, valid);
-    else
-        k_eig_approx<false><<<grid, FA_WARPS * 32, smem, s>>>(img, (uint32_t)pitch, nullptr, 0u, w, h,
-                                                             ctx->d_cand, (uint32_t)ctx->cand_cap,
-                                                             ctx->d_maxlist, (uint32_t)ctx->maxlist_cap,
-                                                             ctx->d_stats, seg, aligned, valid);
+#define FA_LAUNCH(M, B)                                                                                    \
+    k_eig_approx<M, B><<<grid, FA_WARPS * 32, smem, s>>>(img, (uint32_t)pitch, mask, (uint32_t)mask_pitch, w, \
+                                                        h, ctx->d_cand, (uint32_t)ctx->cand_cap,             \
+                                                        ctx->d_maxlist, (uint32_t)ctx->maxlist_cap,          \
+                                                        ctx->d_stats, seg, aligned, valid)
+    if (mask) { if (bps == 5) FA_LAUNCH(true, 5); else FA_LAUNCH(true, 4); }
+    else { if (bps == 5) FA_LAUNCH(false, 5); else FA_LAUNCH(false, 4); }
+#undef FA_LAUNCH
     KR_LAUNCH_CHECK();
     k_exact_max<<<ctx->num_sms * 8, EX_WARPS * 32, 0, s>>>(img, pitch, w, h, scale, tail_start, ctx->d_cand,
                                                            (uint32_t)ctx->cand_cap, ctx->d_maxlist,

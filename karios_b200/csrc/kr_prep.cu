@@ -8,6 +8,8 @@
 //   karios/matcher/klt.py:433-434  cv2.Laplacian(u8, cv2.CV_8U, ksize)
 #include <float.h>
 #include <limits.h>
+#include <stdlib.h>
+#include <type_traits>
 #include "kr_internal.cuh"
 
 namespace {
@@ -478,6 +480,222 @@ k_laplacian2(const T *__restrict__ img, int64_t pitch, int w, int h, const uint8
         lap2_body<K, T, false>(img, pitch, w, h, lut, fmn, frange, invert, out, out_pitch, xs, ys, ye, lane);
 }
 
+// K2, four pixels per lane (k = 3, 5, 7; 8/16-bit rasters with vector-aligned rows,
+// w % 4 == 0, w >= 256, h >= 64): a warp covers 128 columns (120 outputs), a lane holds
+// its pixels as two packed 16-bit pairs A = (p0, p1), B = (p2, p3).  One cascade stage
+// is ONE shuffle and two funnel-shift-adds for four pixels, the 3 x 3 step keeps the
+// running partial E(m-1) - 4 S(m) per pixel, and the clamp + byte pack of four results
+// is two cvt.pack.sat (I2IP) instructions.  The normalisation table of the raster's
+// value range sits in shared memory when that range is below 32 K values (one LDS per
+// pixel instead of a 64-bit address and a global load).  The image border needs no
+// scalar path: the first warp starts 4 columns left of the image and its lane 0 takes
+// lane 1's word with the pixels mirrored (REFLECT_101), the last warp is shifted left to
+// end 4 columns right of the image and its lane 31 mirrors lane 30's word; rows are
+// reflected by index in the top / bottom segments only (ROWFAST elsewhere).
+constexpr int L4_WARPS = 4, L4_VALID = 120, L4_PF = 4, L4_LUT = 32768;
+
+struct L4Raw { uint32_t x, y; };
+template <bool V> struct L4Tag { static constexpr bool value = V; };
+
+template <int K, typename T, bool ROWFAST, bool SLUT>
+__device__ __forceinline__ void lap4_body(const T *__restrict__ img, int64_t pitch, int h,
+                                          const uint8_t *__restrict__ lut, const uint8_t *slut,
+                                          uint32_t base2, uint32_t lim2, int invert,
+                                          uint8_t *__restrict__ out, int64_t out_pitch, int lc, int oc,
+                                          int edge, bool warp_edge, bool store_lane, int ys, int ye)
+{
+    constexpr int R = K / 2;                          // 1, 2, 3
+    constexpr int NS = K - 3;                         // [1,1] stages per dimension: 0, 2, 4
+    constexpr int PF = L4_PF;
+    constexpr bool U8 = sizeof(T) == 1;
+    constexpr unsigned FULL = 0xffffffffu;
+    const int r_first = ys - R;
+    const int n_main = ye - ys;
+
+    // ---- raw rows, PF ahead ----------------------------------------------------
+    const char *pl = (const char *)img + (int64_t)r_first * pitch + (int64_t)lc * sizeof(T);   // ROWFAST
+    const char *pc = (const char *)img + (int64_t)lc * sizeof(T);
+    int r_load = r_first;
+    auto load_next = [&]() -> L4Raw {
+        const char *p;
+        if (ROWFAST) {
+            p = pl;
+            pl += pitch;
+        } else {
+            int tr = r_load;
+            if (tr < 0) tr = -tr;
+            if (tr >= h) tr = 2 * (h - 1) - tr;             // h >= 64: one reflection is enough
+            r_load++;
+            p = pc + (int64_t)tr * pitch;
+        }
+        L4Raw q;
+        if (U8) {
+            q.x = __ldg(reinterpret_cast<const uint32_t *>(p));
+            q.y = 0u;
+            if (warp_edge) {
+                if (edge == 1) q.x = __byte_perm(q.x, q.x, 0x1233);       // (., b3, b2, b1)
+                if (edge == 2) q.x = __byte_perm(q.x, q.x, 0x0012);       // (b2, b1, b0, .)
+            }
+        } else {
+            const uint2 v = __ldg(reinterpret_cast<const uint2 *>(p));
+            q.x = v.x; q.y = v.y;
+            if (warp_edge) {
+                const uint32_t m = __byte_perm(v.y, v.x, 0x7610);          // (p2, p1)
+                if (edge == 1) { q.x = v.y; q.y = m; }                     // (., p3), (p2, p1)
+                if (edge == 2) { q.x = m; q.y = v.x; }                     // (p2, p1), (p0, .)
+            }
+        }
+        return q;
+    };
+    // ---- _to_uint8 of a raw row -> packed pairs ---------------------------------
+    auto lut2 = [&](uint32_t pr) -> uint32_t {
+        uint32_t t0, t1;
+        if (SLUT) {
+            const uint32_t a = __vminu2(pr - base2, lim2);
+            t0 = slut[a & 0xffffu];
+            t1 = slut[a >> 16];
+        } else {
+            t0 = __ldg(lut + (pr & 0xffffu));
+            t1 = __ldg(lut + (pr >> 16));
+        }
+        return __byte_perm(t0, t1, 0x5410);
+    };
+    auto norm = [&](const L4Raw &q, uint32_t &A, uint32_t &B) {
+        if (U8) {
+            const uint32_t v = invert ? ~q.x : q.x;
+            A = __byte_perm(v, 0u, 0x4140);
+            B = __byte_perm(v, 0u, 0x4342);
+        } else {
+            A = lut2(q.x);
+            B = lut2(q.y);
+        }
+    };
+
+    uint32_t vsA[NS > 0 ? NS : 1], vsB[NS > 0 ? NS : 1];
+#pragma unroll
+    for (int i = 0; i < (NS > 0 ? NS : 1); i++) vsA[i] = vsB[i] = 0u;
+    int part[4] = {0, 0, 0, 0}, eprev[4] = {0, 0, 0, 0};
+    uint8_t *po = out + (int64_t)ys * out_pitch + oc;
+
+    L4Raw raw[PF];
+#pragma unroll
+    for (int u = 0; u < PF; u++) raw[u] = load_next();
+    uint32_t nA, nB;
+    norm(raw[0], nA, nB);
+
+    // one input row; ph = its (compile-time) slot in the prefetch ring
+    auto step = [&](auto store_tag, int ph) {
+        constexpr bool STORE = decltype(store_tag)::value;
+        uint32_t A = nA, B = nB;
+        norm(raw[(ph + 1) % PF], nA, nB);
+        raw[ph % PF] = load_next();
+#pragma unroll
+        for (int i = 0; i < NS; i++) {
+            if (i & 1) {                                                   // + (p(x-1), p(x))
+                const uint32_t pb = __shfl_up_sync(FULL, B, 1);
+                const uint32_t tA = A + __funnelshift_r(pb, A, 16);
+                B += __funnelshift_r(A, B, 16);
+                A = tA;
+            } else {                                                       // + (p(x+1), p(x+2))
+                const uint32_t na = __shfl_down_sync(FULL, A, 1);
+                const uint32_t tA = A + __funnelshift_r(A, B, 16);
+                B += __funnelshift_r(B, na, 16);
+                A = tA;
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < NS; i++) {                                     // vertical cascade
+            const uint32_t tA = A + vsA[i], tB = B + vsB[i];
+            vsA[i] = A; vsB[i] = B;
+            A = tA; B = tB;
+        }
+        // S (packed) of row c = r - NS/2; E(x) = S(x-1) + S(x+1)
+        const uint32_t sp = __shfl_up_sync(FULL, B, 1), sn = __shfl_down_sync(FULL, A, 1);
+        const int s0 = (int)(A & 0xffffu), s1 = (int)(A >> 16), s2 = (int)(B & 0xffffu), s3 = (int)(B >> 16);
+        int e[4];
+        e[0] = (int)(sp >> 16) + s1;
+        e[1] = s0 + s2;
+        e[2] = s1 + s3;
+        e[3] = s2 + (int)(sn & 0xffffu);
+        if (STORE) {
+            // out(c-1) = 2 (E(c-2) + E(c)) - 8 S(c-1), saturated to uint8
+            const int o0 = 2 * (part[0] + e[0]), o1 = 2 * (part[1] + e[1]), o2 = 2 * (part[2] + e[2]),
+                      o3 = 2 * (part[3] + e[3]);
+            uint32_t hi, wv;
+            asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(hi) : "r"(o3), "r"(o2), "r"(0));
+            asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(wv) : "r"(o1), "r"(o0), "r"(hi));
+            if (store_lane) *reinterpret_cast<uint32_t *>(po) = wv;
+            po += out_pitch;
+        }
+        part[0] = eprev[0] - 4 * s0; part[1] = eprev[1] - 4 * s1;
+        part[2] = eprev[2] - 4 * s2; part[3] = eprev[3] - 4 * s3;
+#pragma unroll
+        for (int j = 0; j < 4; j++) eprev[j] = e[j];
+    };
+    const L4Tag<false> quiet;
+    const L4Tag<true> storing;
+#pragma unroll
+    for (int i = 0; i < 2 * R; i++) step(quiet, i);
+    constexpr int P0 = (2 * R) % PF;
+    int i = 0;
+    for (; i + PF <= n_main; i += PF) {
+#pragma unroll
+        for (int u = 0; u < PF; u++) step(storing, P0 + u);
+    }
+#pragma unroll
+    for (int u = 0; u < PF - 1; u++)
+        if (i + u < n_main) step(storing, P0 + u);
+}
+
+template <int K, typename T>
+__global__ void __launch_bounds__(L4_WARPS * 32)
+k_laplacian4(const T *__restrict__ img, int64_t pitch, int w, int h, const uint8_t *__restrict__ lut,
+             const KrDevStats *__restrict__ st, int slot, int invert, uint8_t *__restrict__ out,
+             int64_t out_pitch, int seg)
+{
+    extern __shared__ __align__(16) unsigned char l4_smem[];
+    constexpr int R = K / 2;
+    constexpr bool U8 = sizeof(T) == 1;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    // value range of the raster -> table window in shared memory (unsigned 16-bit rasters)
+    bool use_slut = false;
+    uint32_t base2 = 0u, lim2 = 0u;
+    if (!U8 && ((T)-1 > (T)0)) {
+        const int mn = st->min_i[slot], mx = st->max_i[slot];
+        const int base = mn & ~3;
+        if (mn >= 0 && mx >= mn && mx < 65536 && mx - base < L4_LUT) {
+            use_slut = true;                                               // block-uniform
+            const int words = (mx - base) / 4 + 1;
+            const uint32_t *src = reinterpret_cast<const uint32_t *>(lut + base);
+            uint32_t *dst = reinterpret_cast<uint32_t *>(l4_smem);
+            for (int k = threadIdx.x; k < words; k += blockDim.x) dst[k] = __ldg(src + k);
+            base2 = (uint32_t)base * 0x00010001u;
+            lim2 = (uint32_t)(4 * words - 1) * 0x00010001u;
+        }
+    }
+    __syncthreads();
+    const int wx = blockIdx.x * L4_WARPS + wid;
+    int x0 = wx * L4_VALID - 4;                       // first (virtual) column of the warp
+    if (x0 + 4 >= w) return;
+    if (x0 + 128 > w + 4) x0 = w - 124;               // last warp: shifted left, columns overlap
+    const bool left = x0 < 0, right = x0 + 128 > w;
+    int lc = x0 + 4 * lane, edge = 0;
+    if (left && lane == 0) { lc = 0; edge = 1; }
+    if (right && lane == 31) { lc = w - 4; edge = 2; }
+    const bool store_lane = lane >= 1 && lane <= 30;
+    const int ys = blockIdx.y * seg, ye = min(ys + seg, h);
+    const bool rowfast = (ys - R >= 0) && (ye + R + L4_PF <= h);
+#define L4_BODY(RF, SL)                                                                              \
+    lap4_body<K, T, RF, SL>(img, pitch, h, lut, l4_smem, base2, lim2, invert, out, out_pitch, lc,    \
+                            x0 + 4 * lane, edge, left || right, store_lane, ys, ye)
+    if (use_slut) {
+        if (rowfast) L4_BODY(true, true); else L4_BODY(false, true);
+    } else {
+        if (rowfast) L4_BODY(true, false); else L4_BODY(false, false);
+    }
+#undef L4_BODY
+}
+
 template <typename T>
 int launch_minmax(kr_ctx *ctx, const void *a, int64_t pa, const void *b, int64_t pb, int w, int h,
                   int slot_a, int slot_b, int has_nd_a, double nd_a, int has_nd_b, double nd_b,
@@ -521,10 +739,61 @@ int dispatch_minmax(kr_ctx *ctx, const void *a, int64_t pa, const void *b, int64
     }
 }
 
+// rows per block of k_laplacian4: whole waves of co-resident blocks, each segment
+// pays 2R warm-up rows and the table copy (KR_LAP4_SEG overrides, for tuning)
+template <int K, typename T>
+int launch_lap4(kr_ctx *ctx, const void *img, int64_t pitch, int w, int h, int slot, int invert,
+                uint8_t *out, int64_t out_pitch, cudaStream_t s)
+{
+    constexpr int R = K / 2;
+    const size_t smem = (sizeof(T) == 2 && ((T)-1 > (T)0)) ? (size_t)L4_LUT : 0;
+    struct Cfg { int bps, seg; cudaError_t err; };
+    static const Cfg cfg = [smem] {
+        Cfg c;
+        c.bps = 0;
+        c.err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c.bps, k_laplacian4<K, T>, L4_WARPS * 32, smem);
+        if (c.bps < 1) c.bps = 1;
+        const char *e = getenv("KR_LAP4_SEG");
+        c.seg = e ? atoi(e) : 0;
+        return c;
+    }();
+    KR_CUDA(cfg.err);
+    const int bps = cfg.bps, seg_env = cfg.seg;
+    const int nwx = (w + L4_VALID - 1) / L4_VALID, bx = (nwx + L4_WARPS - 1) / L4_WARPS;
+    const int slots = ctx->num_sms * bps;
+    int best_seg = 64;
+    int64_t best_cost = INT64_MAX;
+    for (int waves = 1; waves <= 6; waves++) {
+        int nseg = waves * slots / bx;
+        if (nseg < 1) nseg = 1;
+        int sg = ((h + nseg - 1) / nseg + 3) & ~3;
+        if (sg < 32) sg = 32;
+        const int ns = (h + sg - 1) / sg;
+        const int wv = (bx * ns + slots - 1) / slots;
+        const int64_t cost = (int64_t)wv * (sg + 2 * R + 10);
+        if (cost < best_cost) { best_cost = cost; best_seg = sg; }
+    }
+    const int seg = seg_env > 0 ? ((seg_env + 3) & ~3) : best_seg;
+    dim3 grid(bx, (h + seg - 1) / seg);
+    k_laplacian4<K, T><<<grid, L4_WARPS * 32, smem, s>>>((const T *)img, pitch, w, h, ctx->d_lut[slot],
+                                                        ctx->d_stats, slot, invert, out, out_pitch, seg);
+    KR_LAUNCH_CHECK();
+    return KR_OK;
+}
+
 template <int K, typename T>
 int launch_lap(kr_ctx *ctx, const void *img, int64_t pitch, int w, int h, int slot, int invert,
                uint8_t *out, int64_t out_pitch, cudaStream_t s)
 {
+    if (K >= 3 && K <= 7 && !PixTraits<T>::is_float) {
+        constexpr int K4 = (K >= 3 && K <= 7) ? K : 3;
+        typedef typename std::conditional<PixTraits<T>::is_float, uint16_t, T>::type T4;
+        const size_t va = sizeof(T) * 4;
+        static const bool off = getenv("KR_NO_LAP4") != nullptr;
+        if (!off && w % 4 == 0 && w >= 256 && h >= 64 && (uintptr_t)img % va == 0 && pitch % (int64_t)va == 0 &&
+            (uintptr_t)out % 4 == 0 && out_pitch % 4 == 0)
+            return launch_lap4<K4, T4>(ctx, img, pitch, w, h, slot, invert, out, out_pitch, s);
+    }
     if (K >= 3 && K <= 7) {
         constexpr int K2 = (K >= 3 && K <= 7) ? K : 3;
         constexpr int HL = (K2 / 2 + 1) / 2, VALID = 64 - 4 * HL;

@@ -137,6 +137,42 @@ def case(name, h, w, seed, shift, conf_kw, mask_mode=None, zero_block=False, ext
                  if k in ("p0", "trk_x0", "zncc", "match_ntiles")})
 
 
+def auto_case(name, h, w, seed, shift, conf_kw, negate_mon=False):
+    """KLT.match with laplacian_kernel_size="auto" and / or laplacian_invert_polarity="auto"
+    (klt.py:438-545, 286-304) through the unmodified reference: the per-tile frames, the
+    kernel sizes and polarities it selected per tile, and -- for the first tile -- the
+    inlier ratio of every (mon_ksize, ref_ksize) pair of both polarities."""
+    klt, _, cfg = refimport.load()
+    ref_t, mon_t = synth.make_pair(h, w, seed=seed, shift=shift)
+    ref, mon = _np16(ref_t), _np16(mon_t)
+    if negate_mon:
+        mon = (5000 - mon.astype(np.int32)).astype(np.uint16)
+    conf = conf_of(cfg, **conf_kw)
+    out = dict(ref=ref, mon=mon, h=h, w=w, seed=seed, shift=np.asarray(shift, np.float64))
+    out["conf_json"] = np.array(repr(conf_kw))
+    mon_img, ref_img = refimport.ArrayImage(mon), refimport.ArrayImage(ref)
+    k = klt.KLT(conf)
+    frames = list(k.match(mon_img, ref_img, None))
+    out["match_ntiles"] = len(frames)
+    for i, f in enumerate(frames):
+        out.update(df_cols(f, f"match{i}"))
+    out["tile_ksizes"] = np.array(k._auto_selected_ksizes, np.int64).reshape(-1, 2)
+    out["tile_polarities"] = np.array(k._selected_polarities)
+    out["auto_selected_ksize"] = np.array(k.auto_selected_ksize if k.auto_selected_ksize else (0, 0), np.int64)
+    out["auto_selected_polarity"] = np.array(k.auto_selected_polarity or "")
+    if conf.laplacian_kernel_size == "auto":
+        ts = conf.tile_size
+        mb, rb = mon[:ts, :ts], ref[:ts, :ts]
+        mask_box = ((mb != 0) & (rb != 0)).astype(np.uint8)
+        for label, box in (("normal", mb), ("inverted", 255 - klt._to_uint8(mb))):
+            _, scores, best = klt.KLT(conf)._match_tile_auto_ksize(box, rb, mask_box)
+            out[f"scores_{label}"] = np.array([[a, b, r] for (a, b), r in scores.items()], np.float64)
+            out[f"best_{label}"] = np.array(best if best else (0, 0), np.int64)
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **out)
+    print(name, "tiles", len(frames), "ksizes", out["tile_ksizes"].tolist(), "polarities",
+          out["tile_polarities"].tolist(), "rows", [len(f) for f in frames])
+
+
 def zncc_known_answers():
     """The reference's own ZNCC known-answer cases (tests/test_zncc_service.py,
     tests/test_zncc_zero_std_fix.py) evaluated through the unmodified _zncc2."""
@@ -257,6 +293,14 @@ if __name__ == "__main__":
          dict(laplacian_kernel_size={"mon": 5, "ref": 7}, laplacian_invert_polarity=True,
               matching_winsize=15, outliers_filtering=True, qualityLevel=0.02, minDistance=5,
               blocksize=7, maxCorners=2000), negate_mon=True)
+    # automatic kernel-size and polarity search (klt.py:438-545): two tiles, a contrast-
+    # inverted monitored image (the inverted polarity must win), outlier filter on
+    auto_case("auto_modes", 200, 330, 14, (0.35, -0.25),
+              dict(laplacian_kernel_size="auto", laplacian_invert_polarity="auto", maxCorners=250,
+                   tile_size=200, outliers_filtering=True), negate_mon=True)
+    # automatic kernel size with a fixed polarity, single tile
+    auto_case("auto_ksize", 180, 260, 15, (-0.6, 0.4),
+              dict(laplacian_kernel_size="auto", maxCorners=300, minDistance=6))
     zncc_known_answers()
     mi_golden()
     scene_golden()

@@ -93,6 +93,46 @@ def test_laplacian_dtypes_and_odd_shapes(N, ctx):
     assert not ctx.u8_laplacian(dev(flat), 7).cpu().numpy().any()
 
 
+def test_laplacian_four_pixel_path(N, ctx):
+    """k_laplacian4 (4 pixels per lane; vector-aligned rows, w % 4 == 0, w >= 256, h >= 64):
+    table in shared memory (narrow value range) and in global memory (wide range, int16),
+    uint8 rasters, mirrored first / last lanes, reflected top / bottom rows, windows of a
+    larger raster, every packed kernel size -- bit-exact against the oracle."""
+    rng = np.random.default_rng(11)
+    for shape in ((64, 256), (70, 260), (131, 492), (300, 1000), (517, 724)):
+        narrow = rng.integers(1000, 4000, shape).astype(np.uint16)
+        wide = rng.integers(0, 65535, shape).astype(np.uint16)
+        smooth = (np.add.outer(np.arange(shape[0]) * 7, np.arange(shape[1]) * 3) % 9000 + 500).astype(np.uint16)
+        for a in (narrow, wide, smooth):
+            u8 = O.to_uint8(a)
+            for k in (3, 5, 7):
+                got = ctx.u8_laplacian(dev(a), k).cpu().numpy()
+                want = O.laplacian(u8, k)
+                assert np.array_equal(got, want), (shape, k, int((got != want).sum()))
+        got = ctx.u8_laplacian(dev(narrow), 7, invert=True).cpu().numpy()
+        assert np.array_equal(got, O.laplacian(255 - O.to_uint8(narrow), 7)), shape
+        b = rng.integers(0, 255, shape).astype(np.uint8)
+        for k in (3, 5, 7):
+            assert np.array_equal(ctx.u8_laplacian(dev(b), k).cpu().numpy(), O.laplacian(b, k)), (shape, k)
+        assert np.array_equal(ctx.u8_laplacian(dev(b), 7, invert=True).cpu().numpy(), O.laplacian(255 - b, 7))
+        ai = rng.integers(-3000, 9000, shape).astype(np.int16)
+        assert np.array_equal(ctx.u8_laplacian(dev(ai), 7).cpu().numpy(), O.laplacian(O.to_uint8(ai), 7)), shape
+    # aligned window of a larger raster (tile of a resident scene) and a value range that
+    # straddles a 4-aligned table base
+    big = rng.integers(1003, 1003 + 32000, (400, 1024)).astype(np.uint16)
+    t = dev(big)
+    for (y, x, h, w) in ((0, 0, 400, 1024), (16, 256, 300, 512), (100, 4, 256, 1020)):
+        sub = big[y:y + h, x:x + w]
+        got = ctx.u8_laplacian(t[y:y + h, x:x + w], 7).cpu().numpy()
+        assert np.array_equal(got, O.laplacian(O.to_uint8(sub), 7)), (y, x, h, w)
+    # the context slots (min/max of a previous pass) drive the same kernel
+    a = rng.integers(2000, 2300, (200, 512)).astype(np.uint16)
+    b2 = rng.integers(100, 60000, (200, 512)).astype(np.uint16)
+    ctx.minmax_mask(dev(a), dev(b2))
+    assert np.array_equal(ctx.u8_laplacian(dev(a), 5, slot=0).cpu().numpy(), O.laplacian(O.to_uint8(a), 5))
+    assert np.array_equal(ctx.u8_laplacian(dev(b2), 7, slot=1).cpu().numpy(), O.laplacian(O.to_uint8(b2), 7))
+
+
 @pytest.mark.parametrize("name", CASES)
 def test_min_eigen_val(golden, N, ctx, name):
     g = golden(name)
