@@ -214,6 +214,35 @@ KR_API int kr_match_tile(kr_ctx *ctx, const void *mon, int64_t mon_pitch, const 
                          int has_nodata_mon, double nodata_mon, int has_nodata_ref,
                          double nodata_ref, const kr_klt_conf *conf, kr_rows rows, void *stream);
 
+/* KLT._match_tile_auto_ksize (klt.py:465-545; laplacian_kernel_size == "auto") for one
+ * tile as ONE stream-ordered launch sequence without host synchronisation: min/max (+ auto
+ * mask when mask == NULL), the n_k Laplacians of each raster, their pyramids (once per
+ * plane), goodFeaturesToTrack once per reference kernel size, the n_k * n_k LK round trips
+ * (product order: mon outer, ref inner), the inlier ratios n_kept / n_init, and the winner
+ * -- highest ratio, first maximum wins (strict >, klt.py:536) -- chosen on the device and
+ * its rows (OpenCV corner order, no offsets) copied to `rows`.  invert_mon of `conf` is the
+ * polarity (klt.py:419); ksize_* are ignored.  Not covered here (the caller falls back to
+ * one kr_klt_track per pair): max_corners <= 0, outlier filtering, and a corner pass that
+ * reports select_incomplete (kr_auto_result.redo == 1).
+ * scratch: device memory of kr_auto_ksize_scratch_bytes(); d_result: device record. */
+#define KR_AUTO_MAX_K 8
+typedef struct {
+    int32_t best_mon, best_ref;     /* winning kernel sizes, 0 when no pair produced a result */
+    int32_t n_init, n_kept;         /* Ninit and rows of the winner */
+    int32_t redo;                   /* 1: a corner pass needs the exact re-run -- use the host loop */
+    int32_t n_k;
+    uint64_t valid;                 /* valid pixels of the (auto) mask; 0 => tile skipped */
+    int32_t counts[KR_AUTO_MAX_K * KR_AUTO_MAX_K][2];   /* (n_init, n_kept) per pair, product order */
+} kr_auto_result;
+KR_API int64_t kr_auto_ksize_scratch_bytes(int w, int h, int n_k, int max_corners, int win_size,
+                                           int max_level);
+KR_API int kr_auto_ksize(kr_ctx *ctx, const void *mon, int64_t mon_pitch, const void *ref,
+                         int64_t ref_pitch, int dtype, int w, int h, const uint8_t *mask,
+                         int64_t mask_pitch, int has_nodata_mon, double nodata_mon,
+                         int has_nodata_ref, double nodata_ref, const kr_klt_conf *conf,
+                         const int32_t *ksizes, int n_k, void *scratch, int64_t scratch_bytes,
+                         kr_rows rows, kr_auto_result *d_result, void *stream);
+
 /* ---- full-frame passes either side of the matching path; these
  * take no context. ---- */
 

@@ -23,7 +23,7 @@ EXPORTS = [
     "kr_version", "kr_last_error", "kr_ctx_create", "kr_ctx_destroy", "kr_read_stats",
     "kr_set_select_all", "kr_set_corner_mode", "kr_minmax_mask", "kr_u8_laplacian", "kr_corner_min_eigen_val",
     "kr_good_features", "kr_pyr_down", "kr_pyr_lk", "kr_klt_track", "kr_zncc", "kr_mutual_info",
-    "kr_match_tile",
+    "kr_match_tile", "kr_auto_ksize", "kr_auto_ksize_scratch_bytes",
     "kr_set_profiling", "kr_read_stage_ms",
     "kr_cross_power", "kr_argmax_abs", "kr_shift_image", "kr_histogram", "kr_count_valid",
     "kr_gather_points",
@@ -55,6 +55,16 @@ class Stats(C.Structure):
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+KR_AUTO_MAX_K = 8
+
+
+class AutoResult(C.Structure):
+    """kr_auto_result: outcome of the on-device kernel-size search."""
+    _fields_ = [("best_mon", C.c_int32), ("best_ref", C.c_int32), ("n_init", C.c_int32),
+                ("n_kept", C.c_int32), ("redo", C.c_int32), ("n_k", C.c_int32), ("valid", C.c_uint64),
+                ("counts", (C.c_int32 * 2) * (KR_AUTO_MAX_K * KR_AUTO_MAX_K))]
 
 
 class Rows(C.Structure):
@@ -109,6 +119,9 @@ def load_library(path: str = LIB_PATH):
                                      vp, vp, vp, vp]
         L.kr_match_tile.argtypes = [vp, vp, i64, vp, i64, i32, i32, i32, vp, i64, i32, i32, i32, i32,
                                     i32, f64, i32, f64, C.POINTER(KltConf), Rows, vp]
+        L.kr_auto_ksize_scratch_bytes.argtypes = [i32, i32, i32, i32, i32, i32]
+        L.kr_auto_ksize.argtypes = [vp, vp, i64, vp, i64, i32, i32, i32, vp, i64, i32, f64, i32, f64,
+                                    C.POINTER(KltConf), C.POINTER(C.c_int32), i32, vp, i64, Rows, vp, vp]
         L.kr_cross_power.argtypes = [vp, vp, i64, i32, vp]
         L.kr_argmax_abs.argtypes = [vp, i64, i32, vp, vp, vp]
         L.kr_shift_image.argtypes = [vp, i64, vp, i64, i32, i32, i32, i32, i32, vp]
@@ -116,8 +129,9 @@ def load_library(path: str = LIB_PATH):
         L.kr_count_valid.argtypes = [vp, i64, i32, i32, i32, vp, i64, vp, vp]
         L.kr_gather_points.argtypes = [vp, i64, i32, i32, i32, vp, vp, i32, vp, vp]
         for name in EXPORTS:
-            if name not in ("kr_last_error", "kr_ctx_destroy", "kr_version"):
+            if name not in ("kr_last_error", "kr_ctx_destroy", "kr_version", "kr_auto_ksize_scratch_bytes"):
                 getattr(L, name).restype = i32
+        L.kr_auto_ksize_scratch_bytes.restype = i64
         _lib = L
         return L
 
@@ -368,6 +382,32 @@ class Context:
             self.set_select_all(True)
         self.set_select_all(False)
         return int(st.n_corners), int(st.n_kept)
+
+    def auto_ksize(self, mon, ref, mask, kconf: KltConf, ksizes, rows: RowBuffers,
+                   nodata_mon=None, nodata_ref=None) -> AutoResult:
+        """KLT._match_tile_auto_ksize (klt.py:465-545) on the device: one launch sequence,
+        one synchronisation (the 536-byte result record).  mon / ref: raw tile windows."""
+        h, w = mon.shape
+        ks = (C.c_int32 * len(ksizes))(*[int(k) for k in ksizes])
+        need = int(self.lib.kr_auto_ksize_scratch_bytes(w, h, len(ksizes), int(kconf.max_corners),
+                                                        int(kconf.win_size), int(kconf.max_level)))
+        if need <= 0:
+            raise KariosB200Error("kr_auto_ksize: unsupported configuration")
+        scratch = getattr(self, "_auto_scratch", None)
+        if scratch is None or scratch.numel() < need:
+            scratch = None
+            self._auto_scratch = None
+            scratch = torch.empty(need, dtype=torch.uint8, device=mon.device)
+            self._auto_scratch = scratch
+        rec = torch.zeros(C.sizeof(AutoResult), dtype=torch.uint8, device=mon.device)
+        _check(self.lib.kr_auto_ksize(
+            self._h, mon.data_ptr(), _pitch(mon), ref.data_ptr(), _pitch(ref), dtype_code(mon), w, h,
+            mask.data_ptr() if mask is not None else None, _pitch(mask) if mask is not None else 0,
+            int(nodata_mon is not None), float(nodata_mon or 0.0), int(nodata_ref is not None),
+            float(nodata_ref or 0.0), C.byref(kconf), ks, len(ksizes), scratch.data_ptr(), scratch.numel(),
+            rows.struct(), rec.data_ptr(), _stream()))
+        out = AutoResult.from_buffer_copy(rec.cpu().numpy().tobytes())
+        return out
 
     def zncc(self, ref, mon, x0, y0, dx, dy):
         n = x0.shape[0]

@@ -23,6 +23,72 @@ __global__ void k_set_u32(uint32_t *p, uint32_t v) { *p = v; }
 
 inline int64_t align_up(int64_t v, int64_t a) { return (v + a - 1) / a * a; }
 
+// ---- automatic kernel-size search (kr_auto_ksize) ---------------------------------
+struct AutoKs { int32_t k[KR_AUTO_MAX_K]; };
+
+__global__ void k_auto_begin(kr_auto_result *r, int n_k)
+{
+    r->best_mon = r->best_ref = 0;
+    r->n_init = r->n_kept = 0;
+    r->redo = 0;
+    r->n_k = n_k;
+    r->valid = 0;
+    for (int i = 0; i < KR_AUTO_MAX_K * KR_AUTO_MAX_K; i++) r->counts[i][0] = r->counts[i][1] = 0;
+}
+__global__ void k_auto_valid(kr_auto_result *r, const KrDevStats *st) { r->valid = st->valid; }
+__global__ void k_auto_note_corners(kr_auto_result *r, const KrDevStats *st)
+{
+    if (st->select_incomplete || st->overflow) r->redo = 1;
+}
+__global__ void k_auto_record(kr_auto_result *r, int combo, const int32_t *n_init, const KrDevStats *st)
+{
+    r->counts[combo][0] = *n_init;
+    r->counts[combo][1] = (int32_t)st->n_kept;
+}
+// klt.py:529-539: ratio = len(points) / ninit (Python float division = IEEE double), a pair
+// whose reference plane gave no corners has no result, strict > keeps the first maximum
+__global__ void k_auto_pick(kr_auto_result *r, AutoKs ks, KrDevStats *st)
+{
+    const int n_k = r->n_k;
+    int best = -1;
+    double best_ratio = -1.0;
+    for (int c = 0; c < n_k * n_k; c++) {
+        const int ni = r->counts[c][0], nk = r->counts[c][1];
+        if (ni <= 0) continue;
+        const double ratio = (double)nk / (double)ni;
+        if (ratio > best_ratio) { best_ratio = ratio; best = c; }
+    }
+    if (best >= 0) {
+        r->best_mon = ks.k[best / n_k];
+        r->best_ref = ks.k[best % n_k];
+        r->n_init = r->counts[best][0];
+        r->n_kept = r->counts[best][1];
+    }
+    st->n_corners = (uint32_t)r->n_init;
+    st->n_kept = (uint32_t)r->n_kept;
+}
+__global__ void k_auto_copy(const kr_auto_result *r, AutoKs ks, const float *all_rows, int cap, kr_rows out)
+{
+    const int n_k = r->n_k;
+    if (r->best_mon == 0) return;
+    int im = 0, ir = 0;
+    for (int i = 0; i < n_k; i++) {
+        if (ks.k[i] == r->best_mon) im = i;
+        if (ks.k[i] == r->best_ref) ir = i;
+    }
+    const float *src = all_rows + (size_t)(im * n_k + ir) * 5 * cap;
+    int n = r->n_kept;
+    if (n > out.capacity) n = out.capacity;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        out.x0[i] = src[i];
+        out.y0[i] = src[cap + i];
+        out.dx[i] = src[2 * cap + i];
+        out.dy[i] = src[3 * cap + i];
+        out.score[i] = src[4 * cap + i];
+    }
+}
+
+
 template <typename T> int dev_alloc(T **p, size_t count)
 {
     void *q = nullptr;
@@ -393,6 +459,125 @@ KR_API int kr_mutual_info(kr_ctx *ctx, const void *ref, int64_t ref_pitch, int r
     return krl_mutual_info(ref, ref_pitch, ref_w, ref_h, mon, mon_pitch, mon_w, mon_h, dtype, x0, y0,
                            dx, dy, nullptr, 0.f, n, (const uint32_t *)d_count, out_studholme, out_nmi,
                            (cudaStream_t)stream);
+}
+
+KR_API int64_t kr_auto_ksize_scratch_bytes(int w, int h, int n_k, int max_corners, int win_size,
+                                           int max_level)
+{
+    if (w < 1 || h < 1 || n_k < 1 || n_k > KR_AUTO_MAX_K || max_corners < 1) return 0;
+    int levels, wl[KR_MAX_LEVELS], hl[KR_MAX_LEVELS];
+    int64_t pl[KR_MAX_LEVELS];
+    krl_pyramid_geometry(w, h, align_up(w, 128), win_size, max_level, &levels, wl, hl, pl);
+    int64_t plane = 0;
+    for (int l = 0; l <= levels; l++) plane += align_up(pl[l] * hl[l], 256);
+    const int64_t cap = max_corners;
+    int64_t total = 2ll * n_k * plane;                          // Laplacian planes + pyramids
+    total += (int64_t)n_k * align_up(cap * 2 * 4, 256);         // corners per reference kernel size
+    total += align_up((int64_t)n_k * 4, 256);                   // their counts
+    total += (int64_t)n_k * n_k * align_up(cap * 5 * 4, 256);   // rows per pair
+    return total + 1024;
+}
+
+KR_API int kr_auto_ksize(kr_ctx *ctx, const void *mon, int64_t mon_pitch, const void *ref,
+                         int64_t ref_pitch, int dtype, int w, int h, const uint8_t *mask,
+                         int64_t mask_pitch, int has_nodata_mon, double nodata_mon,
+                         int has_nodata_ref, double nodata_ref, const kr_klt_conf *conf,
+                         const int32_t *ksizes, int n_k, void *scratch, int64_t scratch_bytes,
+                         kr_rows rows, kr_auto_result *d_result, void *stream)
+{
+    KR_TRY(check_dims(ctx, w, h));
+    KR_TRY(check_conf(conf));
+    if (!elem_size(dtype)) return kr_set_error(KR_ERR_UNSUPPORTED, "unsupported raster dtype %d", dtype);
+    if (!mon || !ref || !ksizes || !scratch || !d_result) return kr_set_error(KR_ERR_INVALID, "NULL argument");
+    if (n_k < 1 || n_k > KR_AUTO_MAX_K) return kr_set_error(KR_ERR_INVALID, "n_k %d out of range", n_k);
+    if (conf->max_corners < 1 || conf->max_corners > ctx->corner_cap)
+        return kr_set_error(KR_ERR_UNSUPPORTED, "kr_auto_ksize needs 1 <= maxCorners <= the context's");
+    if (!rows.x0 || !rows.y0 || !rows.dx || !rows.dy || !rows.score || rows.capacity < conf->max_corners)
+        return kr_set_error(KR_ERR_INVALID, "incomplete rows");
+    const int64_t need = kr_auto_ksize_scratch_bytes(w, h, n_k, conf->max_corners, conf->win_size, conf->max_level);
+    if (scratch_bytes < need || (uintptr_t)scratch % 256 != 0)
+        return kr_set_error(KR_ERR_CAPACITY, "scratch of %lld bytes (256-aligned) needed", (long long)need);
+    cudaStream_t s = (cudaStream_t)stream;
+    ctx->last_dtype = dtype;
+    const int cap = conf->max_corners;
+    AutoKs ks;
+    memset(&ks, 0, sizeof(ks));
+    for (int i = 0; i < n_k; i++) ks.k[i] = ksizes[i];
+
+    // ---- scratch layout ----------------------------------------------------------
+    int levels, wl[KR_MAX_LEVELS], hl[KR_MAX_LEVELS];
+    int64_t pl[KR_MAX_LEVELS];
+    krl_pyramid_geometry(w, h, align_up(w, 128), conf->win_size, conf->max_level, &levels, wl, hl, pl);
+    char *cur = (char *)scratch;
+    auto take = [&](int64_t bytes) { char *p = cur; cur += align_up(bytes, 256); return p; };
+    uint8_t *pm[KR_AUTO_MAX_K][KR_MAX_LEVELS], *pr[KR_AUTO_MAX_K][KR_MAX_LEVELS];
+    for (int i = 0; i < n_k; i++)
+        for (int l = 0; l <= levels; l++) pm[i][l] = (uint8_t *)take(pl[l] * hl[l]);
+    for (int i = 0; i < n_k; i++)
+        for (int l = 0; l <= levels; l++) pr[i][l] = (uint8_t *)take(pl[l] * hl[l]);
+    float *p0[KR_AUTO_MAX_K];
+    for (int i = 0; i < n_k; i++) p0[i] = (float *)take((int64_t)cap * 2 * 4);
+    int32_t *cnt = (int32_t *)take((int64_t)n_k * 4);
+    float *all_rows = (float *)cur;
+    // (the rows of the pairs are contiguous: k_auto_copy indexes them as [pair][5][cap])
+
+    k_auto_begin<<<1, 1, 0, s>>>(d_result, n_k);
+    KR_LAUNCH_CHECK();
+    KR_TRY(krl_reset_stats(ctx, s));
+    KR_TRY(krl_minmax_mask(ctx, mon, mon_pitch, ref, ref_pitch, dtype, w, h, has_nodata_mon, nodata_mon,
+                           has_nodata_ref, nodata_ref, mask ? nullptr : ctx->d_mask, ctx->plane_pitch, s));
+    k_auto_valid<<<1, 1, 0, s>>>(d_result, ctx->d_stats);
+    KR_LAUNCH_CHECK();
+    const uint8_t *m = mask ? mask : ctx->d_mask;
+    const int64_t mp = mask ? mask_pitch : ctx->plane_pitch;
+    for (int i = 0; i < n_k; i++) {
+        KR_TRY(krl_laplacian(ctx, mon, mon_pitch, dtype, w, h, 0, ks.k[i], conf->invert_mon, pm[i][0], pl[0], s));
+        KR_TRY(krl_pyramid_plane(pm[i][0], levels, wl, hl, pl, pm[i], s));
+        KR_TRY(krl_laplacian(ctx, ref, ref_pitch, dtype, w, h, 1, ks.k[i], 0, pr[i][0], pl[0], s));
+        KR_TRY(krl_pyramid_plane(pr[i][0], levels, wl, hl, pl, pr[i], s));
+    }
+    for (int i = 0; i < n_k; i++) {
+        KR_TRY(krl_good_features(ctx, pr[i][0], pl[0], m, mp, w, h, conf->max_corners, conf->quality_level,
+                                 conf->min_distance, conf->block_size, conf->tail_mode,
+                                 ctx->force_select_all ? 1 : 0, nullptr, 0, p0[i], cap, cnt + i, s));
+        k_auto_note_corners<<<1, 1, 0, s>>>(d_result, ctx->d_stats);
+        KR_LAUNCH_CHECK();
+    }
+    const float back_thr = (float)conf->back_threshold;
+    for (int im = 0; im < n_k; im++) {
+        for (int ir = 0; ir < n_k; ir++) {
+            KrLkArgs a;
+            memset(&a, 0, sizeof(a));
+            for (int l = 0; l <= levels; l++) {
+                a.img[0][l] = pr[ir][l]; a.img[1][l] = pm[im][l];
+                a.pitch[0][l] = a.pitch[1][l] = pl[l];
+                a.w[l] = wl[l]; a.h[l] = hl[l];
+            }
+            a.levels = levels;
+            a.win = conf->win_size;
+            a.max_count = conf->max_count;
+            a.eps2 = conf->eps * conf->eps;
+            a.min_eig_thr = (float)conf->min_eig_threshold;
+            const uint32_t *n_init = (const uint32_t *)(cnt + ir);
+            KR_TRY(krl_lk_roundtrip(a, p0[ir], cap, n_init, back_thr, ctx->d_p1, ctx->d_d, ctx->d_keep, s));
+            const int combo = im * n_k + ir;
+            float *base = all_rows + (size_t)combo * 5 * cap;
+            kr_rows rc;
+            memset(&rc, 0, sizeof(rc));
+            rc.x0 = base; rc.y0 = base + cap; rc.dx = base + 2 * (size_t)cap; rc.dy = base + 3 * (size_t)cap;
+            rc.score = base + 4 * (size_t)cap;
+            rc.capacity = cap;
+            KR_TRY(krl_emit_rows(ctx, p0[ir], ctx->d_p1, ctx->d_d, ctx->d_keep, cap, n_init, 0, back_thr, 0.f,
+                                 0.f, rc, s));
+            k_auto_record<<<1, 1, 0, s>>>(d_result, combo, cnt + ir, ctx->d_stats);
+            KR_LAUNCH_CHECK();
+        }
+    }
+    k_auto_pick<<<1, 1, 0, s>>>(d_result, ks, ctx->d_stats);
+    KR_LAUNCH_CHECK();
+    k_auto_copy<<<(cap + 255) / 256, 256, 0, s>>>(d_result, ks, all_rows, cap, rows);
+    KR_LAUNCH_CHECK();
+    return KR_OK;
 }
 
 KR_API int kr_match_tile(kr_ctx *ctx, const void *mon, int64_t mon_pitch, const void *ref,

@@ -39,7 +39,12 @@
 
 namespace {
 
-constexpr int FA_WARPS = 4, FA_BLOCKS_PER_SM = 4, FA_OUTW = 104, FA_LEFT = 12, FA_CBUF = 256;
+// One warp per block: every branch of the kernel then depends on blockIdx only, which the
+// compiler knows to be warp-uniform -- with several warps per block the strip index came from
+// threadIdx.x >> 5 and every shuffle was guarded by a convergence check (BRA.DIV + UMOV, 7 %
+// of the issued instructions).  FA_BLOCKS_PER_SM = resident warps per SM: 16 (128 registers
+// per thread) or 20 (96 registers, a few spills; KR_EIG_BPS=4 / 5 selects, 5 is the default).
+constexpr int FA_WARPS = 1, FA_BLOCKS_PER_SM = 20, FA_OUTW = 104, FA_LEFT = 12, FA_CBUF = 256;
 constexpr int FA_RING_I4 = 16 * 32;              // uint4 per warp: 16 rows x 32 lanes of (Dx | Dy << 16) x 4
 constexpr float FA_K1 = 0.04f;                   // >= 1.5 x 64 d, d = 7000 * 2^-24 (Sobel rounding)
 constexpr float FA_K2 = 1.9073486328125e-6f;     // 2^-19 >= 13 * 2^-24 (products, formula, tier-1 float32)
@@ -373,7 +378,7 @@ k_eig_approx(const uint8_t *__restrict__ img, uint32_t pitch, const uint8_t *__r
              const unsigned long long *valid_count)
 {
     extern __shared__ __align__(16) unsigned char fa_smem[];
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int lane = threadIdx.x, wid = 0;                       // FA_WARPS == 1
     uint4 *ring = reinterpret_cast<uint4 *>(fa_smem) + (size_t)wid * FA_RING_I4 + lane;   // [16][32]
     uint64_t *cbuf = reinterpret_cast<uint64_t *>(fa_smem + (size_t)FA_WARPS * FA_RING_I4 * 16) +
                      (size_t)wid * FA_CBUF;
@@ -397,7 +402,7 @@ k_eig_approx(const uint8_t *__restrict__ img, uint32_t pitch, const uint8_t *__r
 // ---------------------------------------------------------------------------
 // Tier 2: OpenCV's arithmetic at single pixels.  One warp per list entry.
 // NB = 1: the pixel itself (max list); NB = 3: its 3 x 3 neighbourhood.
-constexpr int EX_WARPS = 4;
+constexpr int EX_WARPS = 1;           // one warp per block: warp-uniform control flow (see FA_WARPS)
 
 template <int NB> struct ExSmem {
     double col[3 * NB * (14 + NB)];
@@ -516,8 +521,8 @@ k_exact_max(const uint8_t *__restrict__ img, int64_t pitch, int w, int h, float 
             uint32_t maxlist_cap, KrDevStats *st)
 {
     __shared__ ExSmem<1> sm[EX_WARPS];
-    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, warps = (gridDim.x * blockDim.x) >> 5;
+    const int lane = threadIdx.x, wib = 0;                     // EX_WARPS == 1
+    const int warp = blockIdx.x, warps = gridDim.x;
     const uint32_t lenc = st->lmax_enc;
     if (lenc == KR_ENC_NEG_INF) return;                       // no live pixel: fallback decides
     const float lmax = kr_f32_dec_bits(lenc, 0);
@@ -578,9 +583,9 @@ k_exact_cands(const uint8_t *__restrict__ img, int64_t pitch, int w, int h, floa
               KrDevStats *st, uint32_t key_cap)
 {
     __shared__ ExSmem<3> sm[EX_WARPS];
-    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int lane = threadIdx.x, wib = 0;                     // EX_WARPS == 1
     const uint32_t n = min(st->n_sel, key_cap);
-    const int warps = (gridDim.x * blockDim.x) >> 5;
+    const int warps = gridDim.x;
     const uint32_t enc = st->eig_max_enc;
     const float maxv = (enc == KR_ENC_NEG_INF) ? 0.f : kr_f32_dec_bits(enc, 0);
     float thr = (float)((double)maxv * quality);
@@ -591,7 +596,7 @@ k_exact_cands(const uint8_t *__restrict__ img, int64_t pitch, int w, int h, floa
     if (st->cut_applied)
         cut_real = __double2float_ru((double)__uint_as_float(st->cut_bits) * (double)s * (double)s *
                                      (1.0 + 1e-9));
-    for (uint32_t i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < n; i += warps) {
+    for (uint32_t i = blockIdx.x; i < n; i += warps) {
         const uint32_t idx = (uint32_t)sel[i];
         const int y = (int)(idx / (uint32_t)w), x = (int)(idx - (uint32_t)y * (uint32_t)w);
         float vc, vm;
@@ -616,22 +621,32 @@ __global__ void k_commit_exact(KrDevStats *st)
 int krl_eig_fast(kr_ctx *ctx, const uint8_t *img, int64_t pitch, const uint8_t *mask, int64_t mask_pitch,
                  int w, int h, float scale, int tail_start, cudaStream_t s)
 {
-    // resident blocks per SM: 4 (128 registers per thread) or 5 (96), KR_EIG_BPS selects;
+    // resident one-warp blocks per SM: 16 (128 registers per thread) or 20 (96), KR_EIG_BPS=4 / 5;
     // KR_EIG_SMEM_PAD adds unused shared memory per block (caps the residency, for tuning)
-    struct Cfg { int bps; size_t smem; cudaError_t err; };
+    struct Cfg { int bps, occ, seg; size_t smem; cudaError_t err; };
     static const Cfg cfg = [] {
         Cfg c;
         const char *e = getenv("KR_EIG_BPS");
-        c.bps = (e && atoi(e) == 5) ? 5 : FA_BLOCKS_PER_SM;
+        c.bps = (e && atoi(e) == 4) ? 16 : FA_BLOCKS_PER_SM;
         const char *p = getenv("KR_EIG_SMEM_PAD");
         c.smem = (size_t)FA_WARPS * (FA_RING_I4 * 16 + FA_CBUF * 8) + (p ? (size_t)atoi(p) : 0);
-        c.err = cudaFuncSetAttribute(k_eig_approx<true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.smem);
+        c.err = cudaFuncSetAttribute(k_eig_approx<true, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.smem);
         if (c.err == cudaSuccess)
-            c.err = cudaFuncSetAttribute(k_eig_approx<false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.smem);
+            c.err = cudaFuncSetAttribute(k_eig_approx<false, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.smem);
         if (c.err == cudaSuccess)
-            c.err = cudaFuncSetAttribute(k_eig_approx<true, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.smem);
+            c.err = cudaFuncSetAttribute(k_eig_approx<true, 20>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.smem);
         if (c.err == cudaSuccess)
-            c.err = cudaFuncSetAttribute(k_eig_approx<false, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.smem);
+            c.err = cudaFuncSetAttribute(k_eig_approx<false, 20>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.smem);
+        c.occ = c.bps;
+        if (c.err == cudaSuccess) {
+            int o = 0;
+            c.err = (c.bps == 20)
+                ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, k_eig_approx<false, 20>, FA_WARPS * 32, c.smem)
+                : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, k_eig_approx<false, 16>, FA_WARPS * 32, c.smem);
+            if (o >= 1) c.occ = o;
+        }
+        const char *sg = getenv("KR_EIG_SEG");
+        c.seg = sg ? atoi(sg) : 0;
         return c;
     }();
     KR_CUDA(cfg.err);
@@ -642,7 +657,7 @@ int krl_eig_fast(kr_ctx *ctx, const uint8_t *img, int64_t pitch, const uint8_t *
     // rows per warp: whole waves of co-resident blocks; each segment pays 18 warm-up rows
     const int sb = (w + FA_WARPS * FA_OUTW - 1) / (FA_WARPS * FA_OUTW);
     int best_seg = h, best_cost = INT_MAX;
-    const int slots = ctx->num_sms * ((smem > 46 * 1024 && bps > 4) ? 4 : bps);
+    const int slots = ctx->num_sms * cfg.occ;
     const int w0 = (int)(((int64_t)sb * ((h + 255) / 256) + slots - 1) / slots);
     for (int waves = (w0 > 1 ? w0 - 1 : 1); waves <= w0 + 1; waves++) {
         int segs = waves * slots / sb;
@@ -654,7 +669,7 @@ int krl_eig_fast(kr_ctx *ctx, const uint8_t *img, int64_t pitch, const uint8_t *
         int cost = wv * (sg + 18);
         if (cost < best_cost) { best_cost = cost; best_seg = sg; }
     }
-    const int seg = best_seg;
+    const int seg = cfg.seg >= 32 ? cfg.seg : best_seg;
     dim3 grid(sb, (h + seg - 1) / seg);
     // the context's own auto mask: all-valid is known on the device (K1's count)
     const unsigned long long *valid = (mask && mask == ctx->d_mask) ? &ctx->d_stats->valid : nullptr;
@@ -663,11 +678,11 @@ int krl_eig_fast(kr_ctx *ctx, const uint8_t *img, int64_t pitch, const uint8_t *
                                                         h, ctx->d_cand, (uint32_t)ctx->cand_cap,             \
                                                         ctx->d_maxlist, (uint32_t)ctx->maxlist_cap,          \
                                                         ctx->d_stats, seg, aligned, valid)
-    if (mask) { if (bps == 5) FA_LAUNCH(true, 5); else FA_LAUNCH(true, 4); }
-    else { if (bps == 5) FA_LAUNCH(false, 5); else FA_LAUNCH(false, 4); }
+    if (mask) { if (bps == 20) FA_LAUNCH(true, 20); else FA_LAUNCH(true, 16); }
+    else { if (bps == 20) FA_LAUNCH(false, 20); else FA_LAUNCH(false, 16); }
 #undef FA_LAUNCH
     KR_LAUNCH_CHECK();
-    k_exact_max<<<ctx->num_sms * 8, EX_WARPS * 32, 0, s>>>(img, pitch, w, h, scale, tail_start, ctx->d_cand,
+    k_exact_max<<<ctx->num_sms * 32, EX_WARPS * 32, 0, s>>>(img, pitch, w, h, scale, tail_start, ctx->d_cand,
                                                            (uint32_t)ctx->cand_cap, ctx->d_maxlist,
                                                            (uint32_t)ctx->maxlist_cap, ctx->d_stats);
     KR_LAUNCH_CHECK();

@@ -185,6 +185,10 @@ struct KrLkArgs {
 };
 int krl_build_pyramids(kr_ctx *ctx, const uint8_t *prev, int64_t pp, const uint8_t *next, int64_t np_,
                        int w, int h, int win, int max_level, KrLkArgs *args, cudaStream_t s);
+int krl_pyramid_geometry(int w, int h, int64_t pitch, int win, int max_level, int *levels, int *wl,
+                         int *hl, int64_t *pl);
+int krl_pyramid_plane(const uint8_t *src, int levels, const int *wl, const int *hl, const int64_t *pl,
+                      uint8_t *const *dst, cudaStream_t s);
 int krl_lk_single(const KrLkArgs &a, const float *p0, int n, const int32_t *d_count, float *p1,
                   uint8_t *status, float *err, cudaStream_t s);
 int krl_lk_roundtrip(const KrLkArgs &a, const float *p0, int n_cap, const uint32_t *d_count,

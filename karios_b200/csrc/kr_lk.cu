@@ -24,7 +24,7 @@
 namespace {
 
 // ---------------------------------------------------------------- K5 pyrDown
-constexpr int PD_WARPS = 8, PD_ROWS = 32, PD_VALID = 60;
+constexpr int PD_WARPS = 1, PD_ROWS = 64, PD_VALID = 60;   // one warp per block: uniform control flow
 
 struct PyrPair {
     const uint8_t *src[2];
@@ -116,7 +116,7 @@ __global__ void __launch_bounds__(PD_WARPS * 32) k_pyr_down(PyrPair pp, int w, i
     uint8_t *__restrict__ dst = pp.dst[blockIdx.z];
     const int64_t sp = pp.src_pitch[blockIdx.z], dp = pp.dst_pitch[blockIdx.z];
     const int dw = (w + 1) >> 1, dh = (h + 1) >> 1;
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int lane = threadIdx.x, wid = 0;                        // PD_WARPS == 1
     const int xs = (blockIdx.x * PD_WARPS + wid) * PD_VALID;      // first output column of the warp
     if (xs >= dw) return;
     const int oys = blockIdx.y * PD_ROWS, oye = min(oys + PD_ROWS, dh);
@@ -127,13 +127,20 @@ __global__ void __launch_bounds__(PD_WARPS * 32) k_pyr_down(PyrPair pp, int w, i
 }
 
 // --------------------------------------------------------------------- K6 LK
-constexpr int LK_WARPS = 8;
+// One warp per block (and per point): the point index and every trip count derive from
+// blockIdx, which the compiler knows to be warp-uniform -- no convergence guards around the
+// shuffles (with 8 warps per block BRA.DIV / BSSY / BSYNC / UMOV were 9 % of the instructions).
+constexpr int LK_WARPS = 1;
 constexpr int W_BITS = 14;
 
-__device__ __forceinline__ long long warp_sum_ll(long long v)
+// Sum of one int32 per lane as a 64-bit total (the total of 25 lanes can exceed 32 bits):
+// two REDUX instructions on the signed high and the unsigned low half.  The results land in
+// uniform registers, so the convergence tests that follow them are known to be warp-uniform.
+__device__ __forceinline__ long long warp_sum_i32(int v)
 {
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    return v;
+    const int hi = __reduce_add_sync(0xffffffffu, v >> 16);
+    const unsigned lo = __reduce_add_sync(0xffffffffu, (unsigned)v & 0xffffu);
+    return ((long long)hi << 16) + (long long)lo;
 }
 
 __device__ __forceinline__ void lk_weights(float a, float b, int &w00, int &w01, int &w10, int &w11)
@@ -213,8 +220,8 @@ __device__ __forceinline__ void lk_residual(const uint8_t *__restrict__ J, int64
             tvr = vr;
         }
     }
-    o1 = warp_sum_ll((long long)b1);
-    o2 = ABS ? 0ll : warp_sum_ll((long long)b2);
+    o1 = warp_sum_i32(b1);
+    o2 = ABS ? 0ll : warp_sum_i32(b2);
 }
 
 // Template patch of one level: Iw (5 fractional bits), Ix, Iy (Scharr, bilinear at
@@ -274,14 +281,16 @@ __device__ __forceinline__ void lk_patch(const uint8_t *__restrict__ I, int64_t 
         t_dx = dxv; t_dxr = dxr; t_dy = dyv; t_dyr = dyr; t_pv = pv; t_pvr = pvr;
     }
     __syncwarp();
-    S11 = warp_sum_ll((long long)s11);
-    S12 = warp_sum_ll((long long)s12);
-    S22 = warp_sum_ll((long long)s22);
+    S11 = warp_sum_i32(s11);
+    S12 = warp_sum_i32(s12);
+    S22 = warp_sum_i32(s22);
 }
 
 // calcOpticalFlowPyrLK for one point, all levels, direction dir (0: img[0] is
 // the previous image, 1: img[1] is).  Uniform across the warp.
-template <int WIN>
+// WANT_ERR: also the mean absolute residual at the final position (OpenCV's err output;
+// the round trip of klt_tracker never reads it, klt.py:134-144).
+template <int WIN, bool WANT_ERR>
 __device__ void lk_track(const KrLkArgs &A, int dir, float ptx, float pty, float &ox, float &oy,
                          uint8_t &status, float &err, int16_t *sIw, int32_t *sIxy, int lane)
 {
@@ -359,7 +368,7 @@ __device__ void lk_track(const KrLkArgs &A, int dir, float ptx, float pty, float
             }
             pdx = ddx; pdy = ddy;
         }
-        if (status && l == 0) {
+        if (WANT_ERR && status && l == 0) {
             const float ex = __fsub_rn(ox, half), ey = __fsub_rn(oy, half);
             const int iex = (int)floorf(ex), iey = (int)floorf(ey);
             if (iex < -win || iex >= w || iey < -win || iey >= h) {
@@ -389,7 +398,7 @@ k_lk_single(KrLkArgs A, const float *__restrict__ p0, int n, const int32_t *d_co
             float *__restrict__ p1, uint8_t *__restrict__ status, float *__restrict__ err)
 {
     extern __shared__ __align__(16) unsigned char lk_smem[];
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int lane = threadIdx.x, wid = 0;                       // LK_WARPS == 1
     const int ww = A.win * A.win;
     int32_t *sIxy = reinterpret_cast<int32_t *>(lk_smem) + wid * ww;
     int16_t *sIw = reinterpret_cast<int16_t *>(reinterpret_cast<int32_t *>(lk_smem) + LK_WARPS * ww) + wid * ww;
@@ -397,7 +406,7 @@ k_lk_single(KrLkArgs A, const float *__restrict__ p0, int n, const int32_t *d_co
     for (int i = blockIdx.x * LK_WARPS + wid; i < cnt; i += gridDim.x * LK_WARPS) {
         float ox, oy, e;
         uint8_t st;
-        lk_track<WIN>(A, 0, p0[2 * i], p0[2 * i + 1], ox, oy, st, e, sIw, sIxy, lane);
+        lk_track<WIN, true>(A, 0, p0[2 * i], p0[2 * i + 1], ox, oy, st, e, sIw, sIxy, lane);
         if (lane == 0) {
             p1[2 * i] = ox; p1[2 * i + 1] = oy;
             status[i] = st;
@@ -415,7 +424,7 @@ k_lk_roundtrip(KrLkArgs A, const float *__restrict__ p0, int n_cap, const uint32
                uint8_t *__restrict__ keep)
 {
     extern __shared__ __align__(16) unsigned char lk_smem[];
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int lane = threadIdx.x, wid = 0;                       // LK_WARPS == 1
     const int ww = A.win * A.win;
     int32_t *sIxy = reinterpret_cast<int32_t *>(lk_smem) + wid * ww;
     int16_t *sIw = reinterpret_cast<int16_t *>(reinterpret_cast<int32_t *>(lk_smem) + LK_WARPS * ww) + wid * ww;
@@ -424,8 +433,8 @@ k_lk_roundtrip(KrLkArgs A, const float *__restrict__ p0, int n_cap, const uint32
         const float x0 = p0[2 * i], y0 = p0[2 * i + 1];
         float x1, y1, xr, yr, e;
         uint8_t st;
-        lk_track<WIN>(A, 0, x0, y0, x1, y1, st, e, sIw, sIxy, lane);
-        lk_track<WIN>(A, 1, x1, y1, xr, yr, st, e, sIw, sIxy, lane);
+        lk_track<WIN, false>(A, 0, x0, y0, x1, y1, st, e, sIw, sIxy, lane);
+        lk_track<WIN, false>(A, 1, x1, y1, xr, yr, st, e, sIw, sIxy, lane);
         if (lane == 0) {
             float d = fmaxf(fabsf(__fsub_rn(x0, xr)), fabsf(__fsub_rn(y0, yr)));
             p1[2 * i] = x1; p1[2 * i + 1] = y1;
@@ -556,6 +565,49 @@ int krl_build_pyramids(kr_ctx *ctx, const uint8_t *prev, int64_t pp, const uint8
         levels = l + 1;
     }
     a->levels = levels;
+    return KR_OK;
+}
+
+// Level geometry of buildOpticalFlowPyramid for a w x h plane: level l >= 1 has
+// ((w_{l-1} + 1) / 2, (h_{l-1} + 1) / 2), a 128-byte aligned pitch, and is added while both
+// halved sizes exceed the window.  wl / hl / pl: [KR_MAX_LEVELS], entry 0 = the plane itself.
+int krl_pyramid_geometry(int w, int h, int64_t pitch, int win, int max_level, int *levels, int *wl,
+                         int *hl, int64_t *pl)
+{
+    if (max_level >= KR_MAX_LEVELS) max_level = KR_MAX_LEVELS - 1;
+    if (max_level < 0) max_level = 0;
+    wl[0] = w; hl[0] = h; pl[0] = pitch;
+    int n = 0;
+    for (int l = 0; l < max_level; l++) {
+        const int nw = (wl[l] + 1) / 2, nh = (hl[l] + 1) / 2;
+        if (nw <= win || nh <= win) break;
+        wl[l + 1] = nw; hl[l + 1] = nh;
+        pl[l + 1] = ((int64_t)nw + 127) & ~(int64_t)127;
+        n = l + 1;
+    }
+    *levels = n;
+    return KR_OK;
+}
+
+// Levels 1 .. levels of ONE plane into caller-owned planes dst[l] (pitch pl[l]).
+int krl_pyramid_plane(const uint8_t *src, int levels, const int *wl, const int *hl, const int64_t *pl,
+                      uint8_t *const *dst, cudaStream_t s)
+{
+    const uint8_t *cur = src;
+    for (int l = 0; l < levels; l++) {
+        PyrPair q;
+        q.src[0] = q.src[1] = cur;
+        q.dst[0] = q.dst[1] = dst[l + 1];
+        q.src_pitch[0] = q.src_pitch[1] = pl[l];
+        q.dst_pitch[0] = q.dst_pitch[1] = pl[l + 1];
+        const int nw = wl[l + 1], nh = hl[l + 1];
+        dim3 grid((nw + PD_WARPS * PD_VALID - 1) / (PD_WARPS * PD_VALID), (nh + PD_ROWS - 1) / PD_ROWS, 1);
+        const int aligned = ((uintptr_t)cur % 4 == 0) && (pl[l] % 4 == 0) && ((uintptr_t)dst[l + 1] % 2 == 0) &&
+                            (pl[l + 1] % 2 == 0);
+        k_pyr_down<<<grid, PD_WARPS * 32, 0, s>>>(q, wl[l], hl[l], aligned);
+        KR_LAUNCH_CHECK();
+        cur = dst[l + 1];
+    }
     return KR_OK;
 }
 

@@ -120,6 +120,8 @@ class KLT:
         self._tail_mode = tail_mode
         self._auto_selected_ksizes: list[tuple[int, int]] = []
         self._selected_polarities: list[str] = []
+        # "auto" kernel size: the whole search on the device (False: one klt_track per pair)
+        self._batched_auto = True
 
     # ---------------------------------------------------------------- match
     def match(self, mon_img, ref_img, mask) -> Iterator[DataFrame]:
@@ -259,10 +261,47 @@ class KLT:
         ref_l = {k: ctx.u8_laplacian(ref_b, k, invert=False, slot=1) for k in ksizes}
         return m, mon_l, ref_l
 
+    def _auto_ksize_device(self, ctx, mon_t, ref_t, mask_t, win, rows, nd, invert):
+        """The whole search as one device launch sequence (kr_auto_ksize): 10 Laplacians and
+        pyramids, 5 corner sets, 25 LK round trips, ratios and winner on the device; one
+        synchronisation.  -> (DataFrame, Ninit, (mk, rk)) | None | "redo" (host loop needed)."""
+        conf = self._conf
+        x, y, w, h = win
+        mon_b, ref_b = mon_t[y:y + h, x:x + w], ref_t[y:y + h, x:x + w]
+        m = None
+        if mask_t is not None:
+            m = mask_t[y:y + h, x:x + w] if mask_t.shape != (h, w) else mask_t
+            if int(torch.count_nonzero(m).item()) == 0:
+                logger.info("-- No valid pixels, skipping this tile")
+                return None
+        kconf = N.make_conf(conf, ksize_mon=1, ksize_ref=1, invert_mon=invert, tail_mode=self._tail_mode)
+        r = ctx.auto_ksize(mon_b, ref_b, m, kconf, LAPLACIAN_AUTO_CANDIDATES, rows, nd[0], nd[1])
+        if m is None and r.valid == 0:
+            logger.info("-- No valid pixels, skipping this tile")
+            return None
+        if r.redo:
+            return "redo"
+        nk = len(LAPLACIAN_AUTO_CANDIDATES)
+        for i, (mk, rk) in enumerate(itertools.product(LAPLACIAN_AUTO_CANDIDATES, repeat=2)):
+            ni, kept = r.counts[i][0], r.counts[i][1]
+            if ni > 0:
+                logger.info("Auto laplacian: mon_ksize=%s ref_ksize=%s -> inlier ratio=%.3f (%d/%d)",
+                            mk, rk, kept / ni, kept, ni)
+        assert r.n_k == nk
+        if r.best_mon == 0:
+            return None
+        df = _frame(rows.f32[:, : r.n_kept].cpu().numpy(), conf)
+        df.attrs["kr_state"] = "raw"
+        return df, int(r.n_init), (int(r.best_mon), int(r.best_ref))
+
     def _auto_ksize(self, ctx, mon_t, ref_t, mask_t, win, rows, nd, invert):
         """klt.py:465-545: every (mon_ksize, ref_ksize) pair, best inlier ratio,
         first maximum wins (strict >)."""
         conf = self._conf
+        if conf.maxCorners > 0 and not conf.outliers_filtering and self._batched_auto:
+            res = self._auto_ksize_device(ctx, mon_t, ref_t, mask_t, win, rows, nd, invert)
+            if res != "redo":
+                return res
         planes = self._planes(ctx, mon_t, ref_t, mask_t, win, nd, invert, LAPLACIAN_AUTO_CANDIDATES)
         if planes is None:
             logger.info("-- No valid pixels, skipping this tile")

@@ -301,6 +301,11 @@ if __name__ == "__main__":
     # automatic kernel size with a fixed polarity, single tile
     auto_case("auto_ksize", 180, 260, 15, (-0.6, 0.4),
               dict(laplacian_kernel_size="auto", maxCorners=300, minDistance=6))
+    # both searches, no outlier filter (the configuration the on-device search covers), contrast-
+    # inverted monitored image, user-sized tiles with a remainder
+    auto_case("auto_device", 210, 300, 16, (0.25, 0.45),
+              dict(laplacian_kernel_size="auto", laplacian_invert_polarity="auto", maxCorners=200,
+                   tile_size=180, minDistance=8), negate_mon=True)
     zncc_known_answers()
     mi_golden()
     scene_golden()

@@ -272,31 +272,88 @@ def _ksizes(conf):
     return k, k
 
 
+LAPLACIAN_AUTO_CANDIDATES = [3, 5, 7, 9, 11]        # klt.py:39
+
+
+def auto_ksize_search(mon_u8, ref_box, mask_box, conf, acc_mode=0):
+    """KLT._match_tile_auto_ksize (klt.py:465-545): every (mon_ksize, ref_ksize) pair of
+    LAPLACIAN_AUTO_CANDIDATES, corners once per reference kernel size, winner = highest
+    inlier ratio len(points) / Ninit, the first maximum wins (strict >, product order:
+    mon outer, ref inner).  -> ((cols, ninit) | None, scores dict, (mk, rk) | None)."""
+    import itertools
+    ref_u8 = to_uint8(ref_box)
+    mon_l = {k: laplacian(mon_u8, k) for k in LAPLACIAN_AUTO_CANDIDATES}
+    ref_l = {k: laplacian(ref_u8, k) for k in LAPLACIAN_AUTO_CANDIDATES}
+    p0s = {k: good_features(lap, mask_box, conf.maxCorners, conf.qualityLevel, conf.minDistance,
+                            conf.blocksize) for k, lap in ref_l.items()}
+    scores, best, best_ratio, best_k = {}, None, -1.0, None
+    for mk, rk in itertools.product(LAPLACIAN_AUTO_CANDIDATES, repeat=2):
+        p0 = p0s[rk]
+        res = None if p0 is None else klt_tracker(ref_l[rk], mon_l[mk], mask_box, conf, p0=p0,
+                                                  acc_mode=acc_mode)
+        ratio = 0.0
+        if res is not None:
+            cols, ninit = res
+            ratio = len(cols["x0"]) / ninit if ninit > 0 else 0.0
+        scores[(mk, rk)] = ratio
+        if res is not None and ratio > best_ratio:
+            best, best_ratio, best_k = res, ratio, (mk, rk)
+    return best, scores, best_k
+
+
+def track_once(mon_box, ref_box, mask_box, conf, invert_mon, acc_mode=0):
+    """KLT._laplacian_track_once (klt.py:407-436) -> ((cols, ninit) | None, (mk, rk) | None)."""
+    mon_u8 = to_uint8(mon_box)
+    if invert_mon:
+        mon_u8 = 255 - mon_u8
+    if conf.laplacian_kernel_size == "auto":
+        res, _, best_k = auto_ksize_search(mon_u8, ref_box, mask_box, conf, acc_mode)
+        return res, best_k
+    mk, rk = _ksizes(conf)
+    res = klt_tracker(laplacian(to_uint8(ref_box), rk), laplacian(mon_u8, mk), mask_box, conf,
+                      acc_mode=acc_mode)
+    return res, (mk, rk)
+
+
 def match_tile(mon_box, ref_box, mask_box, conf, x_off=0, y_off=0, nd_mon=None, nd_ref=None,
                acc_mode=0):
-    """klt.py:236-349 for int / dict ksize and fixed polarity.  Returns the dict of
-    columns sorted by (x0, y0) with tile offsets applied, or None."""
+    """klt.py:236-349, every kernel-size / polarity mode.  Returns the dict of columns
+    sorted by (x0, y0) with tile offsets applied (plus ninit, ksize, polarity), or None."""
     if mask_box is None:
         mask_box, valid = auto_mask(mon_box, ref_box, nd_mon, nd_ref)
     else:
         valid = int(np.count_nonzero(mask_box > 0))
     if valid == 0:
         return None
-    mk, rk = _ksizes(conf)
-    mon_u8 = to_uint8(mon_box)
-    if conf.laplacian_invert_polarity is True:
-        mon_u8 = 255 - mon_u8
-    lap_mon = laplacian(mon_u8, mk)
-    lap_ref = laplacian(to_uint8(ref_box), rk)
-    res = klt_tracker(lap_ref, lap_mon, mask_box, conf, acc_mode=acc_mode)
+    polarity = None
+    if conf.laplacian_invert_polarity == "auto":
+        # klt.py:286-296, _select_best_polarity :438-463: stable sort on the ratio, the
+        # normal polarity first on ties
+        cands = []
+        for label, inv in (("normal", False), ("inverted", True)):
+            r, ks_ = track_once(mon_box, ref_box, mask_box, conf, inv, acc_mode)
+            if r is None:
+                continue
+            ratio = len(r[0]["x0"]) / r[1] if r[1] > 0 else 0.0
+            cands.append((label, ratio, r, ks_))
+        if not cands:
+            return None
+        cands.sort(key=lambda c: c[1], reverse=True)
+        polarity, _, res, ks = cands[0]
+    else:
+        res, ks = track_once(mon_box, ref_box, mask_box, conf, bool(conf.laplacian_invert_polarity),
+                             acc_mode)
     if res is None:
         return None
     cols, ninit = res
+    cols = dict(cols)
     cols["x0"] = cols["x0"] + np.float32(x_off)
     cols["y0"] = cols["y0"] + np.float32(y_off)
     order = np.lexsort((cols["y0"], cols["x0"]))
     cols = {k: v[order] for k, v in cols.items()}
     cols["ninit"] = ninit
+    cols["ksize"] = ks
+    cols["polarity"] = polarity
     return cols
 
 

@@ -333,6 +333,41 @@ def test_klt_match(golden, name, resident):
         assert np.abs(f["score"].to_numpy() - g[f"match{i}_score"]).max() < 2e-2
 
 
+@pytest.mark.parametrize("name", ["auto_modes", "auto_ksize", "auto_device"])
+@pytest.mark.parametrize("batched", [True, False])
+def test_klt_match_auto_modes(golden, name, batched):
+    """laplacian_kernel_size="auto" / laplacian_invert_polarity="auto" (klt.py:438-545): the
+    on-device search (kr_auto_ksize) and the per-pair host loop select the kernel sizes and
+    polarity the oracle selects (exact-integer LK sums, bit-identical to the CUDA path), return
+    its rows, and agree with the unmodified reference's golden output."""
+    from karios_b200.matcher.klt import KLT
+    from karios_b200.core.configuration import KLTConfiguration
+    from karios_b200.core.image import ArrayRaster
+    g = golden(name)
+    conf = conf_from_golden(g, KLTConfiguration)
+    k = KLT(conf)
+    k._batched_auto = batched
+    frames = list(k.match(ArrayRaster(g["mon"]), ArrayRaster(g["ref"]), None))
+    want = O.match(g["mon"], g["ref"], None, conf_from_golden(g, O.KLTConfiguration), acc_mode=1)
+    assert len(frames) == len(want) == int(g["match_ntiles"])
+    assert [tuple(x) for x in k._auto_selected_ksizes] == [tuple(t["ksize"]) for t in want]
+    if conf.laplacian_invert_polarity == "auto":
+        assert k._selected_polarities == [t["polarity"] for t in want]
+    for f, t in zip(frames, want):
+        assert np.array_equal(f["x0"].to_numpy(), t["x0"]) and np.array_equal(f["y0"].to_numpy(), t["y0"])
+        assert np.abs(f["dx"].to_numpy() - t["dx"]).max() < 1e-3
+        assert np.abs(f["dy"].to_numpy() - t["dy"]).max() < 1e-3
+    # against the reference itself (cv2's float32 sums): same selection on these pairs
+    assert [list(x) for x in k._auto_selected_ksizes] == g["tile_ksizes"].tolist()
+    assert k._selected_polarities == [str(x) for x in g["tile_polarities"]]
+    assert k.auto_selected_ksize == tuple(g["auto_selected_ksize"].tolist())
+    for i, f in enumerate(frames):
+        assert np.array_equal(f["x0"].to_numpy(), g[f"match{i}_x0"])
+        assert np.array_equal(f["y0"].to_numpy(), g[f"match{i}_y0"])
+        assert np.abs(f["dx"].to_numpy() - g[f"match{i}_dx"]).max() < 1e-3
+        assert np.abs(f["dy"].to_numpy() - g[f"match{i}_dy"]).max() < 1e-3
+
+
 @pytest.mark.parametrize("name", CASES)
 def test_zncc(golden, name):
     import pandas as pd

@@ -267,3 +267,40 @@ def test_filter_and_count_restatements():
     xi, yi = x0.astype(int), y0.astype(int)
     want = (mon[yi, xi] != 0) & (ref[yi, xi] != 0) & (mon[yi, xi] != 3)
     assert np.array_equal(keep, want) and 0 < keep.sum() < 200
+
+
+# ------------------------------------------------------------------ a14: automatic modes
+@pytest.mark.parametrize("name", ["auto_modes", "auto_ksize", "auto_device"])
+def test_auto_ksize_and_polarity_match_reference(golden, name):
+    """klt.py:438-545 restated (oracle.auto_ksize_search / track_once / match_tile) against the
+    unmodified reference run by oracle/make_golden.py: the kernel sizes and polarities selected
+    per tile, the inlier ratio of each of the 25 kernel-size pairs, and the winning rows.
+    (OpenCV's float32 accumulation order, acc_mode 0: a back-check decision on a chaotic track of
+    the losing polarity can flip with the exact-integer sums the CUDA path uses.)"""
+    g = golden(name)
+    conf = conf_from_golden(g, O.KLTConfiguration)
+    tiles = O.match(g["mon"], g["ref"], None, conf, acc_mode=0)
+    assert len(tiles) == int(g["match_ntiles"])
+    assert [list(t["ksize"]) for t in tiles] == g["tile_ksizes"].tolist()
+    if conf.laplacian_invert_polarity == "auto":
+        assert [t["polarity"] for t in tiles] == [str(x) for x in g["tile_polarities"]]
+    for i, t in enumerate(tiles):
+        assert np.array_equal(t["x0"], g[f"match{i}_x0"]) and np.array_equal(t["y0"], g[f"match{i}_y0"])
+        assert np.abs(t["dx"] - g[f"match{i}_dx"]).max() < 1e-3
+        assert np.abs(t["dy"] - g[f"match{i}_dy"]).max() < 1e-3
+    # the 25 ratios of the first tile, both polarities where recorded
+    ts = conf.tile_size
+    mon, ref = g["mon"][:ts, :ts], g["ref"][:ts, :ts]
+    mask, _ = O.auto_mask(mon, ref)
+    for label in ("normal", "inverted"):
+        if f"scores_{label}" not in g.files:
+            continue
+        u8 = O.to_uint8(mon)
+        _, scores, best = O.auto_ksize_search(255 - u8 if label == "inverted" else u8, ref, mask, conf, acc_mode=0)
+        want = {(int(a), int(b)): r for a, b, r in g[f"scores_{label}"]}
+        assert scores.keys() == want.keys()
+        # a back-check decision on a chaotic track (wrong polarity) may flip with the last bit of
+        # the float32 sums: at most one pair off by a point or two, the selection unchanged
+        off = [k for k in want if abs(scores[k] - want[k]) >= 1e-12]
+        assert len(off) <= 1 and all(abs(scores[k] - want[k]) <= 0.02 for k in off), (label, off)
+        assert list(best) == g[f"best_{label}"].tolist()
