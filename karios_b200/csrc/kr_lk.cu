@@ -15,16 +15,18 @@
 // One warp tracks one point.  Lane l owns window column l: a window row is one
 // coalesced byte load per lane, horizontal neighbours come from warp shuffles,
 // vertical neighbours from the previous row kept in registers.  The template
-// patch (Iw, Ix, Iy) lives in shared memory (6 B per window pixel); the 2x2
-// system is reduced with integer warp shuffles.
+// patch (Iw, Ix, Iy) lives in shared memory as one 64-bit entry per pixel in rows
+// of 32 (the entries beyond the window are zero, so the lanes beyond it need no
+// masking); the 2x2 system is reduced with two REDUX per sum.
 #include <math.h>
 #include <float.h>
+#include <stdlib.h>
 #include "kr_internal.cuh"
 
 namespace {
 
 // ---------------------------------------------------------------- K5 pyrDown
-constexpr int PD_WARPS = 1, PD_ROWS = 64, PD_VALID = 60;   // one warp per block: uniform control flow
+constexpr int PD_ROWS = 32, PD_VALID = 60;
 
 struct PyrPair {
     const uint8_t *src[2];
@@ -110,20 +112,51 @@ __device__ __forceinline__ void pyr_down_body(const uint8_t *__restrict__ src, i
     }
 }
 
+// Control flow depends on blockIdx only (warp-uniform as far as the compiler can tell, so the
+// shuffles need no convergence guards): the fast / general choice is made per block, and a warp
+// whose strip starts right of the image recomputes the last strip instead of leaving early.
+template <int PD_WARPS>
 __global__ void __launch_bounds__(PD_WARPS * 32) k_pyr_down(PyrPair pp, int w, int h, int aligned)
 {
     const uint8_t *__restrict__ src = pp.src[blockIdx.z];
     uint8_t *__restrict__ dst = pp.dst[blockIdx.z];
     const int64_t sp = pp.src_pitch[blockIdx.z], dp = pp.dst_pitch[blockIdx.z];
     const int dw = (w + 1) >> 1, dh = (h + 1) >> 1;
-    const int lane = threadIdx.x, wid = 0;                        // PD_WARPS == 1
-    const int xs = (blockIdx.x * PD_WARPS + wid) * PD_VALID;      // first output column of the warp
-    if (xs >= dw) return;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int last_xs = ((dw - 1) / PD_VALID) * PD_VALID;         // first output column of the last strip
+    const int xs = min((blockIdx.x * PD_WARPS + wid) * PD_VALID, last_xs);
     const int oys = blockIdx.y * PD_ROWS, oye = min(oys + PD_ROWS, dh);
-    const bool fast = aligned && (2 * xs - 4 >= 0) && (2 * xs - 4 + 128 <= w) && (2 * oys - 2 >= 0) &&
-                      (2 * oye + 6 <= h);
+    const int bx0 = blockIdx.x * PD_WARPS * PD_VALID;             // block: outputs [bx0, bx0 + PD_WARPS * 60)
+    const bool fast = aligned && (2 * bx0 - 4 >= 0) && (2 * (bx0 + (PD_WARPS - 1) * PD_VALID) - 4 + 128 <= w) &&
+                      (bx0 + (PD_WARPS - 1) * PD_VALID <= last_xs) && (2 * oys - 2 >= 0) && (2 * oye + 6 <= h);
     if (fast) pyr_down_body<true>(src, sp, dst, dp, w, h, dw, xs, oys, oye, lane);
     else pyr_down_body<false>(src, sp, dst, dp, w, h, dw, xs, oys, oye, lane);
+}
+
+// warps per block of k_pyr_down: few, so that the blocks holding an image edge (general path
+// for all their warps) stay a small share; KR_PYR_WARPS overrides (1, 2, 4, 8)
+int pyr_warps()
+{
+    static const int v = [] {
+        const char *e = getenv("KR_PYR_WARPS");
+        const int k = e ? atoi(e) : 2;
+        return (k == 1 || k == 2 || k == 4 || k == 8) ? k : 2;
+    }();
+    return v;
+}
+
+int launch_pyr_down(const PyrPair &q, int w, int h, int nw, int nh, int nz, int aligned, cudaStream_t s)
+{
+    const int pw = pyr_warps();
+    dim3 grid((nw + pw * PD_VALID - 1) / (pw * PD_VALID), (nh + PD_ROWS - 1) / PD_ROWS, nz);
+    switch (pw) {
+    case 1: k_pyr_down<1><<<grid, 32, 0, s>>>(q, w, h, aligned); break;
+    case 4: k_pyr_down<4><<<grid, 128, 0, s>>>(q, w, h, aligned); break;
+    case 8: k_pyr_down<8><<<grid, 256, 0, s>>>(q, w, h, aligned); break;
+    default: k_pyr_down<2><<<grid, 64, 0, s>>>(q, w, h, aligned); break;
+    }
+    KR_LAUNCH_CHECK();
+    return KR_OK;
 }
 
 // --------------------------------------------------------------------- K6 LK
@@ -161,15 +194,14 @@ __device__ __forceinline__ void lk_weights(float a, float b, int &w00, int &w01,
 template <bool ABS, bool FAST, int WIN>
 __device__ __forceinline__ void lk_residual(const uint8_t *__restrict__ J, int64_t pJ, int w, int h,
                                             int inx, int iny, int win_rt, int w00, int w01, int w10,
-                                            int w11, const int16_t *sIw, const int32_t *sIxy,
-                                            int lane, long long &o1, long long &o2)
+                                            int w11, const uint2 *sT, int lane, long long &o1,
+                                            long long &o2)
 {
     constexpr unsigned FULL = 0xffffffffu;
     const int win = WIN ? WIN : win_rt;
     const bool act = lane < win;
     const int lc = act ? lane : win;
-    const int16_t *iw = sIw + (act ? lane : 0);
-    const int32_t *ixy = sIxy + (act ? lane : 0);
+    const uint2 *tp = sT + lane;             // row stride 32; columns >= win hold zeros
     int b1 = 0, b2 = 0;
     if (FAST) {
         const uint8_t *p = J + (int64_t)iny * pJ + (inx + lc);
@@ -183,15 +215,14 @@ __device__ __forceinline__ void lk_residual(const uint8_t *__restrict__ J, int64
             if (r < win) vn = __ldg(p + pJ);
             const int vr = __shfl_down_sync(FULL, v, 1);
             const int val = (tv * w00 + tvr * w01 + v * w10 + vr * w11 + (1 << (W_BITS - 5 - 1))) >> (W_BITS - 5);
-            const int o = (r - 1) * win;
-            int diff = val - (int)iw[o];
-            if (!act) diff = 0;
+            const uint2 t = tp[(r - 1) * 32];
+            int diff = val - (int)(int16_t)(t.x & 0xffffu);
             if (ABS) {
+                if (!act) diff = 0;
                 b1 += abs(diff);
-            } else {
-                const int32_t pk = ixy[o];
-                b1 += diff * (int)(int16_t)(pk & 0xffff);
-                b2 += diff * (pk >> 16);
+            } else {                                       // zero gradients beyond the window
+                b1 += diff * ((int)t.x >> 16);
+                b2 += diff * (int)t.y;
             }
             tv = v;
             tvr = vr;
@@ -205,15 +236,14 @@ __device__ __forceinline__ void lk_residual(const uint8_t *__restrict__ J, int64
             const int vr = __shfl_down_sync(FULL, v, 1);
             if (r >= 1) {
                 const int val = (tv * w00 + tvr * w01 + v * w10 + vr * w11 + (1 << (W_BITS - 5 - 1))) >> (W_BITS - 5);
-                const int o = (r - 1) * win;
-                int diff = val - (int)iw[o];
-                if (!act) diff = 0;
+                const uint2 t = tp[(r - 1) * 32];
+                int diff = val - (int)(int16_t)(t.x & 0xffffu);
                 if (ABS) {
+                    if (!act) diff = 0;
                     b1 += abs(diff);
                 } else {
-                    const int32_t pk = ixy[o];
-                    b1 += diff * (int)(int16_t)(pk & 0xffff);
-                    b2 += diff * (pk >> 16);
+                    b1 += diff * ((int)t.x >> 16);
+                    b2 += diff * (int)t.y;
                 }
             }
             tv = v;
@@ -230,8 +260,8 @@ __device__ __forceinline__ void lk_residual(const uint8_t *__restrict__ J, int64
 template <bool FAST, int WIN>
 __device__ __forceinline__ void lk_patch(const uint8_t *__restrict__ I, int64_t pI, int w, int h, int ipx,
                                          int ipy, int win_rt, int w00, int w01, int w10, int w11,
-                                         int16_t *sIw, int32_t *sIxy, int lane, long long &S11,
-                                         long long &S12, long long &S22)
+                                         uint2 *sT, int lane, long long &S11, long long &S12,
+                                         long long &S22)
 {
     constexpr unsigned FULL = 0xffffffffu;
     const int win = WIN ? WIN : win_rt;
@@ -239,8 +269,7 @@ __device__ __forceinline__ void lk_patch(const uint8_t *__restrict__ I, int64_t 
     const int col = FAST ? cx : kr_reflect101(cx, w);
     const bool col_in = FAST || (cx >= 0 && cx < w);
     const bool act = lane >= 1 && lane <= win;
-    int16_t *iw = sIw + (act ? lane - 1 : 0);
-    int32_t *ixy = sIxy + (act ? lane - 1 : 0);
+    uint2 *tp = sT + ((lane + 31) & 31);     // lane l -> column l - 1; lane 0 -> column 31 (zero)
     int a = 0, b = 0, c = 0;
     int t_dx = 0, t_dxr = 0, t_dy = 0, t_dyr = 0, t_pv = 0, t_pvr = 0;
     int s11 = 0, s12 = 0, s22 = 0;
@@ -269,13 +298,13 @@ __device__ __forceinline__ void lk_patch(const uint8_t *__restrict__ I, int64_t 
         const int dxr = __shfl_down_sync(FULL, dxv, 1);
         const int dyr = __shfl_down_sync(FULL, dyv, 1);
         const int pvr = __shfl_down_sync(FULL, pv, 1);
-        if (r >= 3 && act) {
-            const int ix = (t_dx * w00 + t_dxr * w01 + dxv * w10 + dxr * w11 + (1 << (W_BITS - 1))) >> W_BITS;
-            const int iy = (t_dy * w00 + t_dyr * w01 + dyv * w10 + dyr * w11 + (1 << (W_BITS - 1))) >> W_BITS;
-            const int iv = (t_pv * w00 + t_pvr * w01 + pv * w10 + pvr * w11 + (1 << (W_BITS - 5 - 1))) >> (W_BITS - 5);
-            const int o = (r - 3) * win;
-            iw[o] = (int16_t)iv;
-            ixy[o] = (int32_t)((uint32_t)(ix & 0xffff) | ((uint32_t)iy << 16));
+        if (r >= 3) {
+            int ix = (t_dx * w00 + t_dxr * w01 + dxv * w10 + dxr * w11 + (1 << (W_BITS - 1))) >> W_BITS;
+            int iy = (t_dy * w00 + t_dyr * w01 + dyv * w10 + dyr * w11 + (1 << (W_BITS - 1))) >> W_BITS;
+            int iv = (t_pv * w00 + t_pvr * w01 + pv * w10 + pvr * w11 + (1 << (W_BITS - 5 - 1))) >> (W_BITS - 5);
+            if (!act) { ix = 0; iy = 0; iv = 0; }             // columns win .. 31 of the template row
+            // one 64-bit entry per window pixel: Iw (low half) | Ix (high half), Iy
+            tp[(r - 3) * 32] = make_uint2((uint32_t)(iv & 0xffff) | ((uint32_t)ix << 16), (uint32_t)iy);
             s11 += ix * ix; s12 += ix * iy; s22 += iy * iy;
         }
         t_dx = dxv; t_dxr = dxr; t_dy = dyv; t_dyr = dyr; t_pv = pv; t_pvr = pvr;
@@ -292,7 +321,7 @@ __device__ __forceinline__ void lk_patch(const uint8_t *__restrict__ I, int64_t 
 // the round trip of klt_tracker never reads it, klt.py:134-144).
 template <int WIN, bool WANT_ERR>
 __device__ void lk_track(const KrLkArgs &A, int dir, float ptx, float pty, float &ox, float &oy,
-                         uint8_t &status, float &err, int16_t *sIw, int32_t *sIxy, int lane)
+                         uint8_t &status, float &err, uint2 *sT, int lane)
 {
     const int win = WIN ? WIN : A.win;
     const float half = __fmul_rn((float)(win - 1), 0.5f);
@@ -323,9 +352,9 @@ __device__ void lk_track(const KrLkArgs &A, int dir, float ptx, float pty, float
 
         long long S11, S12, S22;
         if (ipx >= 1 && ipy >= 1 && ipx + win + 1 < w && ipy + win + 1 < h)
-            lk_patch<true, WIN>(I, pI, w, h, ipx, ipy, win, w00, w01, w10, w11, sIw, sIxy, lane, S11, S12, S22);
+            lk_patch<true, WIN>(I, pI, w, h, ipx, ipy, win, w00, w01, w10, w11, sT, lane, S11, S12, S22);
         else
-            lk_patch<false, WIN>(I, pI, w, h, ipx, ipy, win, w00, w01, w10, w11, sIw, sIxy, lane, S11, S12, S22);
+            lk_patch<false, WIN>(I, pI, w, h, ipx, ipy, win, w00, w01, w10, w11, sT, lane, S11, S12, S22);
         const float A11 = __fmul_rn((float)S11, FLT_SCALE), A12 = __fmul_rn((float)S12, FLT_SCALE),
                     A22 = __fmul_rn((float)S22, FLT_SCALE);
         float Dt = __fsub_rn(__fmul_rn(A11, A22), __fmul_rn(A12, A12));
@@ -351,9 +380,9 @@ __device__ void lk_track(const KrLkArgs &A, int dir, float ptx, float pty, float
             lk_weights(__fsub_rn(nx, (float)inx), __fsub_rn(ny, (float)iny), w00, w01, w10, w11);
             long long sb1, sb2;
             if (inx >= 0 && iny >= 0 && inx + win < w && iny + win < h)
-                lk_residual<false, true, WIN>(J, pJ, w, h, inx, iny, win, w00, w01, w10, w11, sIw, sIxy, lane, sb1, sb2);
+                lk_residual<false, true, WIN>(J, pJ, w, h, inx, iny, win, w00, w01, w10, w11, sT, lane, sb1, sb2);
             else
-                lk_residual<false, false, WIN>(J, pJ, w, h, inx, iny, win, w00, w01, w10, w11, sIw, sIxy, lane, sb1, sb2);
+                lk_residual<false, false, WIN>(J, pJ, w, h, inx, iny, win, w00, w01, w10, w11, sT, lane, sb1, sb2);
             const float b1 = __fmul_rn((float)sb1, FLT_SCALE), b2 = __fmul_rn((float)sb2, FLT_SCALE);
             const float ddx = __fmul_rn(__fsub_rn(__fmul_rn(A12, b2), __fmul_rn(A22, b1)), Dt);
             const float ddy = __fmul_rn(__fsub_rn(__fmul_rn(A12, b1), __fmul_rn(A11, b2)), Dt);
@@ -377,9 +406,9 @@ __device__ void lk_track(const KrLkArgs &A, int dir, float ptx, float pty, float
                 lk_weights(__fsub_rn(ex, (float)iex), __fsub_rn(ey, (float)iey), w00, w01, w10, w11);
                 long long sabs, dummy;
                 if (iex >= 0 && iey >= 0 && iex + win < w && iey + win < h)
-                    lk_residual<true, true, WIN>(J, pJ, w, h, iex, iey, win, w00, w01, w10, w11, sIw, sIxy, lane, sabs, dummy);
+                    lk_residual<true, true, WIN>(J, pJ, w, h, iex, iey, win, w00, w01, w10, w11, sT, lane, sabs, dummy);
                 else
-                    lk_residual<true, false, WIN>(J, pJ, w, h, iex, iey, win, w00, w01, w10, w11, sIw, sIxy, lane, sabs, dummy);
+                    lk_residual<true, false, WIN>(J, pJ, w, h, iex, iey, win, w00, w01, w10, w11, sT, lane, sabs, dummy);
                 err = __fdiv_rn(__fmul_rn((float)sabs, 1.f), (float)(32 * win * win));
             }
         }
@@ -399,14 +428,12 @@ k_lk_single(KrLkArgs A, const float *__restrict__ p0, int n, const int32_t *d_co
 {
     extern __shared__ __align__(16) unsigned char lk_smem[];
     const int lane = threadIdx.x, wid = 0;                       // LK_WARPS == 1
-    const int ww = A.win * A.win;
-    int32_t *sIxy = reinterpret_cast<int32_t *>(lk_smem) + wid * ww;
-    int16_t *sIw = reinterpret_cast<int16_t *>(reinterpret_cast<int32_t *>(lk_smem) + LK_WARPS * ww) + wid * ww;
+    uint2 *sT = reinterpret_cast<uint2 *>(lk_smem) + wid * 32 * A.win;     // [win][32] template entries
     const int cnt = lk_count(n, d_count);
     for (int i = blockIdx.x * LK_WARPS + wid; i < cnt; i += gridDim.x * LK_WARPS) {
         float ox, oy, e;
         uint8_t st;
-        lk_track<WIN, true>(A, 0, p0[2 * i], p0[2 * i + 1], ox, oy, st, e, sIw, sIxy, lane);
+        lk_track<WIN, true>(A, 0, p0[2 * i], p0[2 * i + 1], ox, oy, st, e, sT, lane);
         if (lane == 0) {
             p1[2 * i] = ox; p1[2 * i + 1] = oy;
             status[i] = st;
@@ -425,16 +452,14 @@ k_lk_roundtrip(KrLkArgs A, const float *__restrict__ p0, int n_cap, const uint32
 {
     extern __shared__ __align__(16) unsigned char lk_smem[];
     const int lane = threadIdx.x, wid = 0;                       // LK_WARPS == 1
-    const int ww = A.win * A.win;
-    int32_t *sIxy = reinterpret_cast<int32_t *>(lk_smem) + wid * ww;
-    int16_t *sIw = reinterpret_cast<int16_t *>(reinterpret_cast<int32_t *>(lk_smem) + LK_WARPS * ww) + wid * ww;
+    uint2 *sT = reinterpret_cast<uint2 *>(lk_smem) + wid * 32 * A.win;     // [win][32] template entries
     int cnt = (int)min(*d_count, (uint32_t)n_cap);
     for (int i = blockIdx.x * LK_WARPS + wid; i < cnt; i += gridDim.x * LK_WARPS) {
         const float x0 = p0[2 * i], y0 = p0[2 * i + 1];
         float x1, y1, xr, yr, e;
         uint8_t st;
-        lk_track<WIN, false>(A, 0, x0, y0, x1, y1, st, e, sIw, sIxy, lane);
-        lk_track<WIN, false>(A, 1, x1, y1, xr, yr, st, e, sIw, sIxy, lane);
+        lk_track<WIN, false>(A, 0, x0, y0, x1, y1, st, e, sT, lane);
+        lk_track<WIN, false>(A, 1, x1, y1, xr, yr, st, e, sT, lane);
         if (lane == 0) {
             float d = fmaxf(fabsf(__fsub_rn(x0, xr)), fabsf(__fsub_rn(y0, yr)));
             p1[2 * i] = x1; p1[2 * i + 1] = y1;
@@ -495,7 +520,7 @@ k_gather_rows(const uint64_t *__restrict__ sorted, const float *__restrict__ p0,
 
 __global__ void k_clear_rowkeys(KrDevStats *st) { st->n_rowkeys = 0; st->n_kept = 0; }
 
-size_t lk_smem_bytes(int win) { return (size_t)LK_WARPS * win * win * 6; }
+size_t lk_smem_bytes(int win) { return (size_t)LK_WARPS * win * 32 * 8; }
 
 int lk_prepare(const KrLkArgs &a, size_t *smem)
 {
@@ -520,12 +545,9 @@ int krl_pyr_down(const uint8_t *src, int64_t pitch, int w, int h, uint8_t *dst, 
     pp.src[0] = pp.src[1] = src; pp.dst[0] = pp.dst[1] = dst;
     pp.src_pitch[0] = pp.src_pitch[1] = pitch; pp.dst_pitch[0] = pp.dst_pitch[1] = dst_pitch;
     int dw = (w + 1) / 2, dh = (h + 1) / 2;
-    dim3 grid((dw + PD_WARPS * PD_VALID - 1) / (PD_WARPS * PD_VALID), (dh + PD_ROWS - 1) / PD_ROWS, 1);
     const int aligned = ((uintptr_t)src % 4 == 0) && (pitch % 4 == 0) && ((uintptr_t)dst % 2 == 0) &&
                         (dst_pitch % 2 == 0);
-    k_pyr_down<<<grid, PD_WARPS * 32, 0, s>>>(pp, w, h, aligned);
-    KR_LAUNCH_CHECK();
-    return KR_OK;
+    return launch_pyr_down(pp, w, h, dw, dh, 1, aligned, s);
 }
 
 // buildOpticalFlowPyramid: a level is added while both halved sizes exceed the window.
@@ -555,13 +577,11 @@ int krl_build_pyramids(kr_ctx *ctx, const uint8_t *prev, int64_t pp, const uint8
         q.dst[0] = ctx->d_pyr[0][l + 1]; q.dst[1] = ctx->d_pyr[1][l + 1];
         q.src_pitch[0] = a->pitch[0][l]; q.src_pitch[1] = a->pitch[1][l];
         q.dst_pitch[0] = q.dst_pitch[1] = pitch;
-        dim3 grid((nw + PD_WARPS * PD_VALID - 1) / (PD_WARPS * PD_VALID), (nh + PD_ROWS - 1) / PD_ROWS, 2);
         int aligned = (pitch % 2 == 0);
         for (int k = 0; k < 2; k++)
             aligned = aligned && ((uintptr_t)q.src[k] % 4 == 0) && (q.src_pitch[k] % 4 == 0) &&
                       ((uintptr_t)q.dst[k] % 2 == 0);
-        k_pyr_down<<<grid, PD_WARPS * 32, 0, s>>>(q, a->w[l], a->h[l], aligned);
-        KR_LAUNCH_CHECK();
+        KR_TRY(launch_pyr_down(q, a->w[l], a->h[l], nw, nh, 2, aligned, s));
         levels = l + 1;
     }
     a->levels = levels;
@@ -601,11 +621,9 @@ int krl_pyramid_plane(const uint8_t *src, int levels, const int *wl, const int *
         q.src_pitch[0] = q.src_pitch[1] = pl[l];
         q.dst_pitch[0] = q.dst_pitch[1] = pl[l + 1];
         const int nw = wl[l + 1], nh = hl[l + 1];
-        dim3 grid((nw + PD_WARPS * PD_VALID - 1) / (PD_WARPS * PD_VALID), (nh + PD_ROWS - 1) / PD_ROWS, 1);
         const int aligned = ((uintptr_t)cur % 4 == 0) && (pl[l] % 4 == 0) && ((uintptr_t)dst[l + 1] % 2 == 0) &&
                             (pl[l + 1] % 2 == 0);
-        k_pyr_down<<<grid, PD_WARPS * 32, 0, s>>>(q, wl[l], hl[l], aligned);
-        KR_LAUNCH_CHECK();
+        KR_TRY(launch_pyr_down(q, wl[l], hl[l], nw, nh, 1, aligned, s));
         cur = dst[l + 1];
     }
     return KR_OK;
