@@ -722,6 +722,111 @@ k_nms(const uint64_t *__restrict__ keys, uint32_t *__restrict__ xy, uint8_t *sta
     }
 }
 
+// K4 without co-residency: the same fixed-point iteration as k_nms, one launch per round.
+// A cooperative grid has to wait until every SM has room for it at the same moment; with
+// several scene pairs in flight (own streams) whose kernels fill all 32 block slots of an SM
+// that wait can stall the whole pipeline.  Plain launches have no such requirement: a round
+// that finds nothing undecided left by its predecessor returns at once.  When NMS_ROUNDS
+// launches do not reach the fixed point (long chains of mutually close candidates),
+// select_incomplete is raised and the caller's exact re-run uses the cooperative kernel.
+constexpr int NMS_ROUNDS = 16;
+
+__global__ void __launch_bounds__(256)
+k_nms_init(const uint64_t *__restrict__ keys, uint32_t *__restrict__ xy, uint8_t *state,
+           int32_t *__restrict__ next, int32_t *head, int w, int cell, int gw, KrDevStats *st,
+           uint32_t key_cap)
+{
+    const uint32_t n = min(st->n_sel, key_cap);
+    const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x, gstride = gridDim.x * blockDim.x;
+    for (uint32_t i = gtid; i < n; i += gstride) {
+        uint32_t idx = (uint32_t)keys[i];
+        uint32_t y = idx / (uint32_t)w, x = idx - y * (uint32_t)w;
+        xy[i] = x | (y << 16);
+        state[i] = 0;
+        int c = (int)(y / cell) * gw + (int)(x / cell);
+        next[i] = atomicExch(&head[c], (int32_t)i);
+    }
+    if (gtid < NMS_ROUNDS) st->nms_pending[gtid] = 0;
+}
+
+// round r: reads the states its predecessors left (plus whatever this round already decided:
+// decisions are final, so a fresher state only saves a round), counts what stays undecided
+__global__ void __launch_bounds__(256)
+k_nms_round(const uint64_t *__restrict__ keys, const uint32_t *__restrict__ xy, uint8_t *state,
+            const int32_t *__restrict__ next, const int32_t *__restrict__ head, int cell, int gw, int gh,
+            double md2, KrDevStats *st, uint32_t key_cap, uint32_t round)
+{
+    if (round > 0 && *((volatile uint32_t *)&st->nms_pending[round - 1]) == 0) return;   // fixed point reached
+    const uint32_t n = min(st->n_sel, key_cap);
+    const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x, gstride = gridDim.x * blockDim.x;
+    volatile uint8_t *vstate = state;
+    uint32_t pending_local = 0;
+    for (uint32_t i = gtid; i < n; i += gstride) {
+        if (vstate[i] != 0) continue;
+        const uint64_t ki = keys[i];
+        const uint32_t p = xy[i];
+        const int x = (int)(p & 0xffffu), y = (int)(p >> 16);
+        const int xc = x / cell, yc = y / cell;
+        const int x1 = max(xc - 1, 0), y1 = max(yc - 1, 0);
+        const int x2 = min(xc + 1, gw - 1), y2 = min(yc + 1, gh - 1);
+        bool rejected = false, pending = false;
+        for (int yy = y1; yy <= y2 && !rejected; yy++)
+            for (int xx = x1; xx <= x2 && !rejected; xx++)
+                for (int32_t j = head[yy * gw + xx]; j >= 0; j = next[j]) {
+                    if ((uint32_t)j == i) continue;
+                    if (keys[j] < ki) continue;                 // lower priority: irrelevant
+                    uint32_t q = xy[j];
+                    int ddx = x - (int)(q & 0xffffu), ddy = y - (int)(q >> 16);
+                    if ((double)(ddx * ddx + ddy * ddy) >= md2) continue;
+                    uint8_t sj = vstate[j];
+                    if (sj == 1) { rejected = true; break; }
+                    if (sj == 0) pending = true;
+                }
+        if (rejected) vstate[i] = 2;
+        else if (!pending) vstate[i] = 1;
+        else pending_local++;
+    }
+    unsigned any = __ballot_sync(0xffffffffu, pending_local != 0);
+    if ((threadIdx.x & 31) == 0 && any) atomicAdd(&st->nms_pending[round], 1u);
+    if (gtid == 0) st->nms_rounds = round + 1;
+}
+
+__global__ void __launch_bounds__(256)
+k_nms_compact(const uint64_t *__restrict__ keys, const uint8_t *__restrict__ state,
+              uint64_t *__restrict__ accepted, KrDevStats *st, uint32_t key_cap)
+{
+    __shared__ uint32_t s_cnt[8];
+    __shared__ uint32_t s_base;
+    const uint32_t n = min(st->n_sel, key_cap);
+    const uint32_t gstride = gridDim.x * blockDim.x;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    for (uint32_t i0 = blockIdx.x * blockDim.x; i0 < n; i0 += gstride) {
+        uint32_t i = i0 + threadIdx.x;
+        bool keep = (i < n) && (state[i] == 1);
+        unsigned bal = __ballot_sync(0xffffffffu, keep);
+        if (lane == 0) s_cnt[wid] = __popc(bal);
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            uint32_t tot = 0;
+            for (int k = 0; k < 8; k++) { uint32_t c = s_cnt[k]; s_cnt[k] = tot; tot += c; }
+            s_base = tot ? atomicAdd(&st->n_acc, tot) : 0;
+        }
+        __syncthreads();
+        if (keep) accepted[s_base + s_cnt[wid] + __popc(bal & ((1u << lane) - 1))] = keys[i];
+        __syncthreads();
+    }
+}
+
+__global__ void k_nms_final(KrDevStats *st, uint32_t max_corners)
+{
+    const uint32_t nacc = st->n_acc;
+    const bool enough = (max_corners > 0) && (nacc >= max_corners);
+    const bool cut_short = st->fast_mode ? (st->cut_applied != 0) : (st->n_sel < st->n_thr);
+    if (!enough && cut_short) st->select_incomplete = 1;
+    // no fixed point within NMS_ROUNDS launches: undecided candidates were left out
+    if (st->nms_pending[NMS_ROUNDS - 1] != 0) st->select_incomplete = 1;
+}
+
 // minDistance < 1: OpenCV skips the grid and takes the sorted list as is.
 __global__ void k_accept_all(const uint64_t *__restrict__ keys, uint64_t *__restrict__ accepted,
                              KrDevStats *st, uint32_t key_cap)
@@ -909,10 +1014,26 @@ int krl_good_features(kr_ctx *ctx, const uint8_t *img, int64_t pitch, const uint
         KrDevStats *st = ctx->d_stats;
         uint32_t key_cap = cap, mc = (max_corners > 0) ? (uint32_t)max_corners : 0u;
         uint32_t max_rounds = 1u << 20;
-        void *args[] = {&keys, &xy, &state, &next, &head, &acc, &w, &cell, &gw, &gh,
-                        &md2, &st, &key_cap, &mc, &max_rounds};
-        KR_CUDA(cudaLaunchCooperativeKernel((const void *)k_nms, dim3(ctx->nms_grid), dim3(256), args,
-                                            0, s));
+        if (select_all || ctx->force_select_all) {
+            // exact re-run / unlimited corners: any number of rounds, co-resident grid
+            void *args[] = {&keys, &xy, &state, &next, &head, &acc, &w, &cell, &gw, &gh,
+                            &md2, &st, &key_cap, &mc, &max_rounds};
+            KR_CUDA(cudaLaunchCooperativeKernel((const void *)k_nms, dim3(ctx->nms_grid), dim3(256), args,
+                                                0, s));
+        } else {
+            const int ng = ctx->num_sms * 2;
+            k_nms_init<<<ng, 256, 0, s>>>(keys, xy, state, next, head, w, cell, gw, st, key_cap);
+            KR_LAUNCH_CHECK();
+            for (int r = 0; r < NMS_ROUNDS; r++) {
+                k_nms_round<<<ng, 256, 0, s>>>(keys, xy, state, next, head, cell, gw, gh, md2, st, key_cap,
+                                              (uint32_t)r);
+                KR_LAUNCH_CHECK();
+            }
+            k_nms_compact<<<ng, 256, 0, s>>>(keys, state, acc, st, key_cap);
+            KR_LAUNCH_CHECK();
+            k_nms_final<<<1, 1, 0, s>>>(st, mc);
+            KR_LAUNCH_CHECK();
+        }
     } else {
         k_accept_all<<<sgrid, 256, 0, s>>>(ctx->d_keys_a, ctx->d_keys_b, ctx->d_stats, cap);
         KR_LAUNCH_CHECK();

@@ -34,6 +34,7 @@ struct KrDevStats {
     uint32_t cut_applied;               // the value cut-off dropped candidates above the threshold
     uint32_t fast_mode, fast_fallback;  // two-tier path in use / it cannot decide: re-run exactly
     uint32_t pad[2];
+    uint32_t nms_pending[16];           // multi-launch NMS: candidates left undecided by round r
 };
 
 struct kr_ctx {
@@ -180,6 +181,7 @@ struct KrLkArgs {
     int w[KR_MAX_LEVELS], h[KR_MAX_LEVELS];
     int levels;                             // top level index (0 = no pyramid)
     int win, max_count;
+    int use_cache;                          // J window cache in shared memory (set by lk_prepare)
     double eps2;
     float min_eig_thr;
 };

@@ -201,7 +201,8 @@ __device__ __forceinline__ void lk_residual(const uint8_t *__restrict__ J, int64
     const int win = WIN ? WIN : win_rt;
     const bool act = lane < win;
     const int lc = act ? lane : win;
-    const uint2 *tp = sT + lane;             // row stride 32; columns >= win hold zeros
+    const int ts = win + 1;                  // template row stride; column `win` is a zero pad
+    const uint2 *tp = sT + lc;               // lanes beyond the window read the pad
     int b1 = 0, b2 = 0;
     if (FAST) {
         const uint8_t *p = J + (int64_t)iny * pJ + (inx + lc);
@@ -215,7 +216,7 @@ __device__ __forceinline__ void lk_residual(const uint8_t *__restrict__ J, int64
             if (r < win) vn = __ldg(p + pJ);
             const int vr = __shfl_down_sync(FULL, v, 1);
             const int val = (tv * w00 + tvr * w01 + v * w10 + vr * w11 + (1 << (W_BITS - 5 - 1))) >> (W_BITS - 5);
-            const uint2 t = tp[(r - 1) * 32];
+            const uint2 t = tp[(r - 1) * ts];
             int diff = val - (int)(int16_t)(t.x & 0xffffu);
             if (ABS) {
                 if (!act) diff = 0;
@@ -236,7 +237,7 @@ __device__ __forceinline__ void lk_residual(const uint8_t *__restrict__ J, int64
             const int vr = __shfl_down_sync(FULL, v, 1);
             if (r >= 1) {
                 const int val = (tv * w00 + tvr * w01 + v * w10 + vr * w11 + (1 << (W_BITS - 5 - 1))) >> (W_BITS - 5);
-                const uint2 t = tp[(r - 1) * 32];
+                const uint2 t = tp[(r - 1) * ts];
                 int diff = val - (int)(int16_t)(t.x & 0xffffu);
                 if (ABS) {
                     if (!act) diff = 0;
@@ -254,6 +255,59 @@ __device__ __forceinline__ void lk_residual(const uint8_t *__restrict__ J, int64
     o2 = ABS ? 0ll : warp_sum_i32(b2);
 }
 
+// The window of J around the current position, cached in shared memory: the iterations of one
+// level move it by a fraction of a pixel, so after the first (cold) fill every iteration reads
+// its win + 1 rows from shared memory -- with 30 warps of windows per SM the L1 keeps under a
+// third of the re-read sectors.  Region: (win + 1 + 2 LK_M)^2 bytes, row stride 32, origin
+// (cx0, cy0); used while the integer origin of the window stays within the margin.
+constexpr int LK_M = 2;
+
+template <int WIN>
+__device__ __forceinline__ void lk_fill_cache(const uint8_t *__restrict__ J, int64_t pJ, int cx0, int cy0,
+                                              int win_rt, uint8_t *sJ, int lane)
+{
+    const int win = WIN ? WIN : win_rt;
+    const int side = win + 1 + 2 * LK_M;               // <= 32
+    const uint8_t *p = J + (int64_t)cy0 * pJ + cx0 + min(lane, side - 1);
+    __syncwarp();
+#pragma unroll 6
+    for (int r = 0; r < side; r++) {
+        sJ[r * 32 + lane] = __ldg(p);
+        p += pJ;
+    }
+    __syncwarp();
+}
+
+template <int WIN>
+__device__ __forceinline__ void lk_residual_cached(const uint8_t *sJw, int win_rt, int w00, int w01, int w10,
+                                                   int w11, const uint2 *sT, int lane, long long &o1,
+                                                   long long &o2)
+{
+    constexpr unsigned FULL = 0xffffffffu;
+    const int win = WIN ? WIN : win_rt;
+    const int lc = lane < win ? lane : win;
+    const int ts = win + 1;
+    const uint2 *tp = sT + lc;
+    const uint8_t *p = sJw + lc;                        // window origin inside the cache
+    int b1 = 0, b2 = 0;
+    int tv = p[0];
+    int tvr = __shfl_down_sync(FULL, tv, 1);
+#pragma unroll 5
+    for (int r = 1; r <= win; r++) {
+        const int v = p[r * 32];
+        const int vr = __shfl_down_sync(FULL, v, 1);
+        const int val = (tv * w00 + tvr * w01 + v * w10 + vr * w11 + (1 << (W_BITS - 5 - 1))) >> (W_BITS - 5);
+        const uint2 t = tp[(r - 1) * ts];
+        const int diff = val - (int)(int16_t)(t.x & 0xffffu);
+        b1 += diff * ((int)t.x >> 16);
+        b2 += diff * (int)t.y;
+        tv = v;
+        tvr = vr;
+    }
+    o1 = warp_sum_i32(b1);
+    o2 = warp_sum_i32(b2);
+}
+
 // Template patch of one level: Iw (5 fractional bits), Ix, Iy (Scharr, bilinear at
 // the sub-pixel origin) into shared memory, and the sums of Ix^2, IxIy, Iy^2.
 // lane <-> image column ipx - 1 + lane; rows stream through registers.
@@ -269,7 +323,9 @@ __device__ __forceinline__ void lk_patch(const uint8_t *__restrict__ I, int64_t 
     const int col = FAST ? cx : kr_reflect101(cx, w);
     const bool col_in = FAST || (cx >= 0 && cx < w);
     const bool act = lane >= 1 && lane <= win;
-    uint2 *tp = sT + ((lane + 31) & 31);     // lane l -> column l - 1; lane 0 -> column 31 (zero)
+    const bool wr = lane >= 1 && lane <= win + 1;      // lane l -> column l - 1; lane win + 1 -> the zero pad
+    const int ts = win + 1;
+    uint2 *tp = sT + (wr ? lane - 1 : 0);
     int a = 0, b = 0, c = 0;
     int t_dx = 0, t_dxr = 0, t_dy = 0, t_dyr = 0, t_pv = 0, t_pvr = 0;
     int s11 = 0, s12 = 0, s22 = 0;
@@ -302,9 +358,9 @@ __device__ __forceinline__ void lk_patch(const uint8_t *__restrict__ I, int64_t 
             int ix = (t_dx * w00 + t_dxr * w01 + dxv * w10 + dxr * w11 + (1 << (W_BITS - 1))) >> W_BITS;
             int iy = (t_dy * w00 + t_dyr * w01 + dyv * w10 + dyr * w11 + (1 << (W_BITS - 1))) >> W_BITS;
             int iv = (t_pv * w00 + t_pvr * w01 + pv * w10 + pvr * w11 + (1 << (W_BITS - 5 - 1))) >> (W_BITS - 5);
-            if (!act) { ix = 0; iy = 0; iv = 0; }             // columns win .. 31 of the template row
+            if (!act) { ix = 0; iy = 0; iv = 0; }             // the pad column
             // one 64-bit entry per window pixel: Iw (low half) | Ix (high half), Iy
-            tp[(r - 3) * 32] = make_uint2((uint32_t)(iv & 0xffff) | ((uint32_t)ix << 16), (uint32_t)iy);
+            if (wr) tp[(r - 3) * ts] = make_uint2((uint32_t)(iv & 0xffff) | ((uint32_t)ix << 16), (uint32_t)iy);
             s11 += ix * ix; s12 += ix * iy; s22 += iy * iy;
         }
         t_dx = dxv; t_dxr = dxr; t_dy = dyv; t_dyr = dyr; t_pv = pv; t_pvr = pvr;
@@ -315,13 +371,27 @@ __device__ __forceinline__ void lk_patch(const uint8_t *__restrict__ I, int64_t 
     S22 = warp_sum_i32(s22);
 }
 
+// DRAM -> L2 hint for the rows a level is about to read (lane <-> row, both ends of the row
+// segment); coordinates are clamped into the image, so every address is valid.
+__device__ __forceinline__ void lk_prefetch_rows(const uint8_t *__restrict__ img, int64_t pitch, int w, int h,
+                                                 int x0, int y0, int cols, int rows, int lane)
+{
+    if (lane < rows) {
+        const int y = min(max(y0 + lane, 0), h - 1);
+        const int xa = min(max(x0, 0), w - 1), xb = min(max(x0 + cols - 1, 0), w - 1);
+        const uint8_t *row = img + (int64_t)y * pitch;
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(row + xa));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(row + xb));
+    }
+}
+
 // calcOpticalFlowPyrLK for one point, all levels, direction dir (0: img[0] is
 // the previous image, 1: img[1] is).  Uniform across the warp.
 // WANT_ERR: also the mean absolute residual at the final position (OpenCV's err output;
 // the round trip of klt_tracker never reads it, klt.py:134-144).
 template <int WIN, bool WANT_ERR>
 __device__ void lk_track(const KrLkArgs &A, int dir, float ptx, float pty, float &ox, float &oy,
-                         uint8_t &status, float &err, uint2 *sT, int lane)
+                         uint8_t &status, float &err, uint2 *sT, uint8_t *sJ, int lane)
 {
     const int win = WIN ? WIN : A.win;
     const float half = __fmul_rn((float)(win - 1), 0.5f);
@@ -347,6 +417,17 @@ __device__ void lk_track(const KrLkArgs &A, int dir, float ptx, float pty, float
             if (l == 0) { status = 0; err = 0.f; }
             continue;
         }
+        // the template rows of this level and the window of J at the start position are
+        // requested now; the next finer level's rows too (its position is about twice this one)
+        lk_prefetch_rows(I, pI, w, h, ipx - 1, ipy - 1, win + 3, win + 3, lane);
+        lk_prefetch_rows(J, pJ, w, h, (int)floorf(__fsub_rn(nx, half)) - LK_M, (int)floorf(__fsub_rn(ny, half)) - LK_M,
+                         win + 1 + 2 * LK_M, win + 1 + 2 * LK_M, lane);
+        if (l > 0) {
+            const int fx = 2 * ipx - 2, fy = 2 * ipy - 2;
+            lk_prefetch_rows(A.img[dir][l - 1], A.pitch[dir][l - 1], A.w[l - 1], A.h[l - 1], fx, fy, win + 6, 32, lane);
+            lk_prefetch_rows(A.img[dir ^ 1][l - 1], A.pitch[dir ^ 1][l - 1], A.w[l - 1], A.h[l - 1], fx, fy, win + 6,
+                             32, lane);
+        }
         int w00, w01, w10, w11;
         lk_weights(__fsub_rn(px, (float)ipx), __fsub_rn(py, (float)ipy), w00, w01, w10, w11);
 
@@ -371,6 +452,8 @@ __device__ void lk_track(const KrLkArgs &A, int dir, float ptx, float pty, float
         // ---- iterations on J ----------------------------------------------
         nx = __fsub_rn(nx, half); ny = __fsub_rn(ny, half);
         float pdx = 0.f, pdy = 0.f;
+        bool cached = false;                       // J window cache of this level / direction
+        int cx0 = 0, cy0 = 0;
         for (int j = 0; j < A.max_count; j++) {
             const int inx = (int)floorf(nx), iny = (int)floorf(ny);
             if (inx < -win || inx >= w || iny < -win || iny >= h) {
@@ -379,10 +462,24 @@ __device__ void lk_track(const KrLkArgs &A, int dir, float ptx, float pty, float
             }
             lk_weights(__fsub_rn(nx, (float)inx), __fsub_rn(ny, (float)iny), w00, w01, w10, w11);
             long long sb1, sb2;
-            if (inx >= 0 && iny >= 0 && inx + win < w && iny + win < h)
-                lk_residual<false, true, WIN>(J, pJ, w, h, inx, iny, win, w00, w01, w10, w11, sT, lane, sb1, sb2);
-            else
+            if (inx >= 0 && iny >= 0 && inx + win < w && iny + win < h) {
+                bool hit = cached && (unsigned)(inx - cx0) <= 2u * LK_M && (unsigned)(iny - cy0) <= 2u * LK_M;
+                if (!hit && A.use_cache) {
+                    const int ncx = inx - LK_M, ncy = iny - LK_M, side = win + 1 + 2 * LK_M;
+                    if (ncx >= 0 && ncy >= 0 && ncx + side <= w && ncy + side <= h) {
+                        lk_fill_cache<WIN>(J, pJ, ncx, ncy, win, sJ, lane);
+                        cx0 = ncx; cy0 = ncy;
+                        cached = hit = true;
+                    }
+                }
+                if (hit)
+                    lk_residual_cached<WIN>(sJ + (iny - cy0) * 32 + (inx - cx0), win, w00, w01, w10, w11, sT, lane,
+                                            sb1, sb2);
+                else
+                    lk_residual<false, true, WIN>(J, pJ, w, h, inx, iny, win, w00, w01, w10, w11, sT, lane, sb1, sb2);
+            } else {
                 lk_residual<false, false, WIN>(J, pJ, w, h, inx, iny, win, w00, w01, w10, w11, sT, lane, sb1, sb2);
+            }
             const float b1 = __fmul_rn((float)sb1, FLT_SCALE), b2 = __fmul_rn((float)sb2, FLT_SCALE);
             const float ddx = __fmul_rn(__fsub_rn(__fmul_rn(A12, b2), __fmul_rn(A22, b1)), Dt);
             const float ddy = __fmul_rn(__fsub_rn(__fmul_rn(A12, b1), __fmul_rn(A11, b2)), Dt);
@@ -428,12 +525,14 @@ k_lk_single(KrLkArgs A, const float *__restrict__ p0, int n, const int32_t *d_co
 {
     extern __shared__ __align__(16) unsigned char lk_smem[];
     const int lane = threadIdx.x, wid = 0;                       // LK_WARPS == 1
-    uint2 *sT = reinterpret_cast<uint2 *>(lk_smem) + wid * 32 * A.win;     // [win][32] template entries
+    uint2 *sT = reinterpret_cast<uint2 *>(lk_smem);                        // [win][win + 1] template entries
+    uint8_t *sJ = lk_smem + (size_t)A.win * (A.win + 1) * 8;               // [win + 1 + 2 LK_M][32] window cache
+    (void)wid;
     const int cnt = lk_count(n, d_count);
     for (int i = blockIdx.x * LK_WARPS + wid; i < cnt; i += gridDim.x * LK_WARPS) {
         float ox, oy, e;
         uint8_t st;
-        lk_track<WIN, true>(A, 0, p0[2 * i], p0[2 * i + 1], ox, oy, st, e, sT, lane);
+        lk_track<WIN, true>(A, 0, p0[2 * i], p0[2 * i + 1], ox, oy, st, e, sT, sJ, lane);
         if (lane == 0) {
             p1[2 * i] = ox; p1[2 * i + 1] = oy;
             status[i] = st;
@@ -452,14 +551,16 @@ k_lk_roundtrip(KrLkArgs A, const float *__restrict__ p0, int n_cap, const uint32
 {
     extern __shared__ __align__(16) unsigned char lk_smem[];
     const int lane = threadIdx.x, wid = 0;                       // LK_WARPS == 1
-    uint2 *sT = reinterpret_cast<uint2 *>(lk_smem) + wid * 32 * A.win;     // [win][32] template entries
+    uint2 *sT = reinterpret_cast<uint2 *>(lk_smem);                        // [win][win + 1] template entries
+    uint8_t *sJ = lk_smem + (size_t)A.win * (A.win + 1) * 8;               // [win + 1 + 2 LK_M][32] window cache
+    (void)wid;
     int cnt = (int)min(*d_count, (uint32_t)n_cap);
     for (int i = blockIdx.x * LK_WARPS + wid; i < cnt; i += gridDim.x * LK_WARPS) {
         const float x0 = p0[2 * i], y0 = p0[2 * i + 1];
         float x1, y1, xr, yr, e;
         uint8_t st;
-        lk_track<WIN, false>(A, 0, x0, y0, x1, y1, st, e, sT, lane);
-        lk_track<WIN, false>(A, 1, x1, y1, xr, yr, st, e, sT, lane);
+        lk_track<WIN, false>(A, 0, x0, y0, x1, y1, st, e, sT, sJ, lane);
+        lk_track<WIN, false>(A, 1, x1, y1, xr, yr, st, e, sT, sJ, lane);
         if (lane == 0) {
             float d = fmaxf(fabsf(__fsub_rn(x0, xr)), fabsf(__fsub_rn(y0, yr)));
             p1[2 * i] = x1; p1[2 * i + 1] = y1;
@@ -520,10 +621,19 @@ k_gather_rows(const uint64_t *__restrict__ sorted, const float *__restrict__ p0,
 
 __global__ void k_clear_rowkeys(KrDevStats *st) { st->n_rowkeys = 0; st->n_kept = 0; }
 
-size_t lk_smem_bytes(int win) { return (size_t)LK_WARPS * win * 32 * 8; }
-
-int lk_prepare(const KrLkArgs &a, size_t *smem)
+bool lk_cache_enabled(int win)
 {
+    static const bool off = getenv("KR_LK_NOCACHE") != nullptr;
+    return !off && win + 1 + 2 * LK_M <= 32;
+}
+size_t lk_smem_bytes(int win)
+{
+    return (size_t)LK_WARPS * ((size_t)win * (win + 1) * 8 + (lk_cache_enabled(win) ? (size_t)(win + 1 + 2 * LK_M) * 32 : 0));
+}
+
+int lk_prepare(KrLkArgs &a, size_t *smem)
+{
+    a.use_cache = lk_cache_enabled(a.win) ? 1 : 0;
     if (a.win < 3 || a.win > 29)
         return kr_set_error(KR_ERR_UNSUPPORTED, "LK window %d not supported (3..29)", a.win);
     *smem = lk_smem_bytes(a.win);
@@ -629,9 +739,10 @@ int krl_pyramid_plane(const uint8_t *src, int levels, const int *wl, const int *
     return KR_OK;
 }
 
-int krl_lk_single(const KrLkArgs &a, const float *p0, int n, const int32_t *d_count, float *p1,
+int krl_lk_single(const KrLkArgs &a_in, const float *p0, int n, const int32_t *d_count, float *p1,
                   uint8_t *status, float *err, cudaStream_t s)
 {
+    KrLkArgs a = a_in;
     size_t smem;
     KR_TRY(lk_prepare(a, &smem));
     if (n <= 0) return KR_OK;
@@ -642,9 +753,10 @@ int krl_lk_single(const KrLkArgs &a, const float *p0, int n, const int32_t *d_co
     return KR_OK;
 }
 
-int krl_lk_roundtrip(const KrLkArgs &a, const float *p0, int n_cap, const uint32_t *d_count,
+int krl_lk_roundtrip(const KrLkArgs &a_in, const float *p0, int n_cap, const uint32_t *d_count,
                      float back_thr, float *p1, float *dist, uint8_t *keep, cudaStream_t s)
 {
+    KrLkArgs a = a_in;
     size_t smem;
     KR_TRY(lk_prepare(a, &smem));
     if (n_cap <= 0) return KR_OK;

@@ -1,0 +1,24 @@
+#!/bin/bash
+mkdir -p gpurun_out
+run() { # name, env...
+  name=$1; shift
+  env "$@" timeout 300 python bench.py --quick --steps 16 --warmup 4 ${BENCH_ARGS} > gpurun_out/bench_$name.json 2> gpurun_out/bench_$name.err
+  python - "$name" <<'PY'
+import json, sys
+name = sys.argv[1]
+try:
+    d = json.loads(open(f"gpurun_out/bench_{name}.json").read().strip().splitlines()[-1])
+    st = {k: v["ms"] for k, v in d["stages"].items()}
+    print(name, "ms/pair", round(d["ms_per_step"], 4), "pairs/s", round(d["scene_pairs_per_sec"], 1), "lk", st["lk_roundtrip"], "nms", st["nms"], flush=True)
+except Exception as e:
+    print(name, "FAILED", e, open(f"gpurun_out/bench_{name}.err").read()[-800:])
+PY
+}
+for i in 1 2; do
+BENCH_ARGS="--depth 4" run d4_$i X=1
+BENCH_ARGS="--depth 6" run d6_$i X=1
+BENCH_ARGS="--depth 8" run d8_$i X=1
+BENCH_ARGS="--depth 4" run d4nc_$i KR_LK_NOCACHE=1
+BENCH_ARGS="--depth 6" run d6nc_$i KR_LK_NOCACHE=1
+BENCH_ARGS="--depth 8" run d8nc_$i KR_LK_NOCACHE=1
+done
