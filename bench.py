@@ -226,6 +226,7 @@ def cuda_arm(args):
         scenes.append((mon, ref))
     torch.cuda.synchronize()
     sm = SceneMatcher(size, size, conf, 0.4, device=dev, depth=args.depth)
+    sm.trace_units = bool(os.environ.get("KR_TRACE_UNITS"))
 
     from karios_b200 import sharding
 
@@ -262,6 +263,21 @@ def cuda_arm(args):
     e1.record()
     torch.cuda.synchronize()
     sampler.stop_flag.set()
+    # host-side view of the timed region: exact re-runs (select_incomplete) and the largest gap
+    # between two finished units (a stalled host thread or device shows up here)
+    if getattr(sm, "unit_events", None):
+        ev = sm.unit_events
+        base = ev[0][0]
+        tl = [(round(base.elapsed_time(a), 3), round(base.elapsed_time(b), 3), round(1e3 * (t1 - t0), 3)) for a, b, t0, t1 in ev]
+        h0 = ev[0][2]
+        print("UNIT TIMELINE (gpu start ms, gpu end ms, host enqueue ms, host t ms):", file=sys.stderr)
+        for (a, b, q), e in zip(tl, ev):
+            print(f"  {a:9.3f} {b:9.3f} dur {b - a:8.3f}  enq {q:7.3f}  host_t {1e3 * (e[2] - h0):9.3f}", file=sys.stderr)
+    done_t = list(getattr(sm, "unit_done_t", []))
+    gaps = [b - a for a, b in zip(done_t, done_t[1:])]
+    pipeline_diag = {"redo_units": int(getattr(sm, "n_redo", 0)), "redo_flags": list(getattr(sm, "redo_flags", []))[:4],
+                     "max_unit_gap_ms": round(1e3 * max(gaps), 3) if gaps else None,
+                     "median_unit_gap_ms": round(1e3 * float(np.median(gaps)), 3) if gaps else None}
     ms = e0.elapsed_time(e1)
     if world > 1:
         dist.barrier()
@@ -452,7 +468,7 @@ def cuda_arm(args):
             "cpu_baseline": cpu,
             "e2e": e2e,
             "next_rows": next_rows,
-            "gpu_launches": 28 * args.steps * len(sm.windows),      # own kernels per tile (profiles/ncu_launches_*.csv)
+            "pipeline": pipeline_diag, "gpu_launches": 28 * args.steps * len(sm.windows),      # own kernels per tile (profiles/ncu_launches_*.csv)
             "clocks": sampler.summary(),
             "stats_last": {k: v for k, v in st.as_dict().items() if k.startswith("n_") or k == "nms_rounds"},
         }

@@ -12,6 +12,8 @@ of the next pair with the matching of the current one.
 """
 from __future__ import annotations
 
+import time
+
 import numpy as np
 import torch
 from pandas import DataFrame
@@ -88,6 +90,19 @@ class SceneMatcher:
         slot is needed again, so up to `depth` units overlap on the device.
         -> (list per pair of per-tile (rows, zncc[, mi]) tuples, total rows)."""
         results, total = [], 0
+        pairs = list(pairs)
+        # One result arena for the whole call, allocated before any unit is in flight: nothing
+        # inside the pipelined loop touches the allocator (a cudaMalloc of the caching allocator
+        # while four units are in flight was measured to stall the host for 10-40 ms).
+        n_units = len(pairs) * len(self.windows)
+        cap = self.rows.capacity
+        arena_f32 = torch.empty((max(n_units, 1), 5, cap), dtype=torch.float32, device=self.device)
+        arena_z = torch.empty((max(n_units, 1), cap), dtype=torch.float64, device=self.device)
+        arena_mi = torch.empty((max(n_units, 1), 2, cap), dtype=torch.float64, device=self.device) \
+            if self.with_mi else None
+        self.n_redo, self.redo_flags, self.unit_done_t = 0, [], []     # diagnostics of the last call
+        self.unit_events = []
+        self.trace_units = getattr(self, "trace_units", False)
         inflight = [None] * self.depth
         cur = torch.cuda.current_stream(self.device)
 
@@ -98,21 +113,26 @@ class SceneMatcher:
                 return
             inflight[slot] = None
             ctx, rows, stream = self._slots[slot]
-            pair_idx, mon, ref, win = job
+            pair_idx, mon, ref, win, unit = job
             with torch.cuda.stream(stream):
                 st = ctx.read_stats()
+                self.unit_done_t.append(time.perf_counter())
                 if st.select_incomplete:          # rare: redo with every candidate
+                    self.n_redo += 1
+                    self.redo_flags.append((int(st.two_tier_fallback), int(st.overflow), int(st.n_corners),
+                                            int(st.n_sorted), int(st.nms_rounds)))
                     st = ctx.match_tile(mon, ref, mask, win, self.kconf, rows, nodata[0], nodata[1])
                 n = int(st.n_kept)
                 if (mask is None and st.valid == 0) or st.n_corners == 0:
                     return
                 total += n
                 if collect:
-                    t = (rows.f32[:, :n].clone(), rows.zncc[:n].clone())
+                    t = (arena_f32[unit, :, :n], arena_z[unit, :n])
+                    t[0].copy_(rows.f32[:, :n])
+                    t[1].copy_(rows.zncc[:n])
                     if self.with_mi:
-                        t = t + (rows.mi[:, :n].clone(),)
-                    for x in t:
-                        x.record_stream(cur)
+                        t = t + (arena_mi[unit, :, :n],)
+                        t[2].copy_(rows.mi[:, :n])
                     results[pair_idx].append(t)
 
         k = 0
@@ -124,8 +144,15 @@ class SceneMatcher:
                 ctx, rows, stream = self._slots[slot]
                 stream.wait_stream(cur)
                 with torch.cuda.stream(stream):
+                    if self.trace_units:
+                        ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+                        ev[0].record()
+                        t_enq = time.perf_counter()
                     ctx.match_tile_async(mon, ref, mask, win, self.kconf, rows, nodata[0], nodata[1])
-                inflight[slot] = (pair_idx, mon, ref, win)
+                    if self.trace_units:
+                        ev[1].record()
+                        self.unit_events.append(ev + (t_enq, time.perf_counter()))
+                inflight[slot] = (pair_idx, mon, ref, win, k)
                 k += 1
         for j in range(self.depth):
             finalise((k + j) % self.depth)

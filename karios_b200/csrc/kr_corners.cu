@@ -18,6 +18,7 @@
 // early exit.
 #include <limits.h>
 #include <math.h>
+#include <stdlib.h>
 #include "kr_internal.cuh"
 
 namespace {
@@ -722,12 +723,10 @@ k_nms(const uint64_t *__restrict__ keys, uint32_t *__restrict__ xy, uint8_t *sta
     }
 }
 
-// K4 without co-residency: the same fixed-point iteration as k_nms, one launch per round.
-// A cooperative grid has to wait until every SM has room for it at the same moment; with
-// several scene pairs in flight (own streams) whose kernels fill all 32 block slots of an SM
-// that wait can stall the whole pipeline.  Plain launches have no such requirement: a round
-// that finds nothing undecided left by its predecessor returns at once.  When NMS_ROUNDS
-// launches do not reach the fixed point (long chains of mutually close candidates),
+// K4 without co-residency (KR_NMS_PLAIN=1; measured slower than the cooperative kernel, 0.139
+// vs 0.088 ms, kept as an alternative): the same fixed-point iteration as k_nms, one launch per
+// round; a round that finds nothing undecided left by its predecessor returns at once.  When
+// NMS_ROUNDS launches do not reach the fixed point (long chains of mutually close candidates),
 // select_incomplete is raised and the caller's exact re-run uses the cooperative kernel.
 constexpr int NMS_ROUNDS = 16;
 
@@ -1014,8 +1013,10 @@ int krl_good_features(kr_ctx *ctx, const uint8_t *img, int64_t pitch, const uint
         KrDevStats *st = ctx->d_stats;
         uint32_t key_cap = cap, mc = (max_corners > 0) ? (uint32_t)max_corners : 0u;
         uint32_t max_rounds = 1u << 20;
-        if (select_all || ctx->force_select_all) {
-            // exact re-run / unlimited corners: any number of rounds, co-resident grid
+        static const bool plain_nms = getenv("KR_NMS_PLAIN") != nullptr;
+        if (!plain_nms || select_all || ctx->force_select_all) {
+            // default, and always for the exact re-run / unlimited corners: any number of rounds,
+            // co-resident grid
             void *args[] = {&keys, &xy, &state, &next, &head, &acc, &w, &cell, &gw, &gh,
                             &md2, &st, &key_cap, &mc, &max_rounds};
             KR_CUDA(cudaLaunchCooperativeKernel((const void *)k_nms, dim3(ctx->nms_grid), dim3(256), args,
