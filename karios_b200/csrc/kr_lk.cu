@@ -98,11 +98,14 @@ __device__ __forceinline__ void pyr_down_body(const uint8_t *__restrict__ src, i
     };
 
     uint32_t h0 = pd_hsum(load_next()), h1 = pd_hsum(load_next()), h2 = pd_hsum(load_next());
-    // four input rows (two output rows) are requested one iteration ahead
+    // four input rows (two output rows) per iteration, requested two iterations ahead
     uint32_t n0 = load_next(), n1 = load_next(), n2 = load_next(), n3 = load_next();
+    uint32_t m0 = 0, m1 = 0, m2 = 0, m3 = 0;
+    if (oys + 2 < oye) { m0 = load_next(); m1 = load_next(); m2 = load_next(); m3 = load_next(); }
     for (int oy = oys; oy < oye; oy += 2) {
         const uint32_t c0 = n0, c1 = n1, c2 = n2, c3 = n3;
-        if (oy + 2 < oye) { n0 = load_next(); n1 = load_next(); n2 = load_next(); n3 = load_next(); }
+        n0 = m0; n1 = m1; n2 = m2; n3 = m3;
+        if (oy + 4 < oye) { m0 = load_next(); m1 = load_next(); m2 = load_next(); m3 = load_next(); }
         // packed 16-bit pairs: (h0 + h4) + 4 (h1 + h3) + 6 h2 <= 16 * 4080 = 65280 per field
         const uint32_t h3 = pd_hsum(c0), h4 = pd_hsum(c1);
         store_next(h0 + h4 + 4u * (h1 + h3) + 6u * h2 + 0x00800080u);
@@ -371,20 +374,6 @@ __device__ __forceinline__ void lk_patch(const uint8_t *__restrict__ I, int64_t 
     S22 = warp_sum_i32(s22);
 }
 
-// DRAM -> L2 hint for the rows a level is about to read (lane <-> row, both ends of the row
-// segment); coordinates are clamped into the image, so every address is valid.
-__device__ __forceinline__ void lk_prefetch_rows(const uint8_t *__restrict__ img, int64_t pitch, int w, int h,
-                                                 int x0, int y0, int cols, int rows, int lane)
-{
-    if (lane < rows) {
-        const int y = min(max(y0 + lane, 0), h - 1);
-        const int xa = min(max(x0, 0), w - 1), xb = min(max(x0 + cols - 1, 0), w - 1);
-        const uint8_t *row = img + (int64_t)y * pitch;
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(row + xa));
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(row + xb));
-    }
-}
-
 // calcOpticalFlowPyrLK for one point, all levels, direction dir (0: img[0] is
 // the previous image, 1: img[1] is).  Uniform across the warp.
 // WANT_ERR: also the mean absolute residual at the final position (OpenCV's err output;
@@ -416,17 +405,6 @@ __device__ void lk_track(const KrLkArgs &A, int dir, float ptx, float pty, float
         if (ipx < -win || ipx >= w || ipy < -win || ipy >= h) {
             if (l == 0) { status = 0; err = 0.f; }
             continue;
-        }
-        // the template rows of this level and the window of J at the start position are
-        // requested now; the next finer level's rows too (its position is about twice this one)
-        lk_prefetch_rows(I, pI, w, h, ipx - 1, ipy - 1, win + 3, win + 3, lane);
-        lk_prefetch_rows(J, pJ, w, h, (int)floorf(__fsub_rn(nx, half)) - LK_M, (int)floorf(__fsub_rn(ny, half)) - LK_M,
-                         win + 1 + 2 * LK_M, win + 1 + 2 * LK_M, lane);
-        if (l > 0) {
-            const int fx = 2 * ipx - 2, fy = 2 * ipy - 2;
-            lk_prefetch_rows(A.img[dir][l - 1], A.pitch[dir][l - 1], A.w[l - 1], A.h[l - 1], fx, fy, win + 6, 32, lane);
-            lk_prefetch_rows(A.img[dir ^ 1][l - 1], A.pitch[dir ^ 1][l - 1], A.w[l - 1], A.h[l - 1], fx, fy, win + 6,
-                             32, lane);
         }
         int w00, w01, w10, w11;
         lk_weights(__fsub_rn(px, (float)ipx), __fsub_rn(py, (float)ipy), w00, w01, w10, w11);
