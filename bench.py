@@ -234,10 +234,9 @@ def cuda_arm(args):
     wtab, _ = sm.match_many([scenes[i % len(scenes)] for i in range(args.warmup)])
     if world > 1:
         # warm-up of the exchange step too (NCCL sets its channels up on the first collective)
-        wp = [torch.cat([sharding.pack_rows(t_[0], t_[1]) for t_ in t]) if t else
-              torch.zeros((0, 6), dtype=torch.float64, device=dev) for t in wtab]
-        sharding.gather_matches([rank + i * world for i in range(len(wp))], wp, world * len(wp))
-        sharding.gather_moments(torch.cat(wp))
+        _, wown = sharding.gather_units([rank + i * world for i in range(len(wtab))], sm.last_arena[0],
+                                        sm.last_arena[1], sm.last_counts, world * len(wtab))
+        sharding.gather_moments(wown)
     del wtab
     torch.cuda.synchronize()
     if world > 1:
@@ -249,16 +248,16 @@ def cuda_arm(args):
     # K steps = K scene pairs, `depth` of them in flight (each on its own context
     # and stream); every pair's rows are collected
     tables, matches = sm.match_many([scenes[i % len(scenes)] for i in range(args.steps)])
+    e_mid = torch.cuda.Event(enable_timing=True)
+    e_mid.record()
     if world > 1:
         # the one exchange step of the path: every rank ends with the match tables of
         # all world*steps scene pairs (all_reduce of counts + NCCL all_gather of rows)
         # and the global dx/dy moments
         n_units = world * args.steps
         ids = [rank + i * world for i in range(args.steps)]
-        packed = [torch.cat([sharding.pack_rows(t_[0], t_[1]) for t_ in t]) if t else
-                  torch.zeros((0, 6), dtype=torch.float64, device=dev) for t in tables]
-        merged = sharding.gather_matches(ids, packed, n_units)
-        sharding.gather_moments(torch.cat(packed))
+        merged, own = sharding.gather_units(ids, sm.last_arena[0], sm.last_arena[1], sm.last_counts, n_units)
+        sharding.gather_moments(own)
         assert len(merged) == n_units
     e1.record()
     torch.cuda.synchronize()
@@ -279,6 +278,7 @@ def cuda_arm(args):
                      "max_unit_gap_ms": round(1e3 * max(gaps), 3) if gaps else None,
                      "median_unit_gap_ms": round(1e3 * float(np.median(gaps)), 3) if gaps else None}
     ms = e0.elapsed_time(e1)
+    exchange_ms = e_mid.elapsed_time(e1) if world > 1 else 0.0
     if world > 1:
         dist.barrier()
         t = torch.tensor([ms, float(matches)], device=dev, dtype=torch.float64)
@@ -468,7 +468,7 @@ def cuda_arm(args):
             "cpu_baseline": cpu,
             "e2e": e2e,
             "next_rows": next_rows,
-            "pipeline": pipeline_diag, "gpu_launches": 28 * args.steps * len(sm.windows),      # own kernels per tile (profiles/ncu_launches_*.csv)
+            "pipeline": pipeline_diag, "exchange_ms": round(exchange_ms, 3), "gpu_launches": 28 * args.steps * len(sm.windows),      # own kernels per tile (profiles/ncu_launches_*.csv)
             "clocks": sampler.summary(),
             "stats_last": {k: v for k, v in st.as_dict().items() if k.startswith("n_") or k == "nms_rounds"},
         }

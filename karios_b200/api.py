@@ -103,6 +103,8 @@ class SceneMatcher:
         self.n_redo, self.redo_flags, self.unit_done_t = 0, [], []     # diagnostics of the last call
         self.unit_events = []
         self.trace_units = getattr(self, "trace_units", False)
+        # the arena and the rows per unit of the last call (sharding.gather_units packs from here)
+        self.last_arena, self.last_counts = (arena_f32, arena_z, arena_mi), [0] * n_units
         inflight = [None] * self.depth
         cur = torch.cuda.current_stream(self.device)
 
@@ -126,6 +128,7 @@ class SceneMatcher:
                 if (mask is None and st.valid == 0) or st.n_corners == 0:
                     return
                 total += n
+                self.last_counts[unit] = n if collect else 0
                 if collect:
                     t = (arena_f32[unit, :, :n], arena_z[unit, :n])
                     t[0].copy_(rows.f32[:, :n])

@@ -50,6 +50,39 @@ def gather_matches(unit_ids: Sequence[int], unit_rows: Sequence[torch.Tensor], n
     return [allr[u % world, u // world, : cnt[u]] for u in range(n_units)]
 
 
+def gather_units(unit_ids: Sequence[int], arena_f32: torch.Tensor, arena_z: torch.Tensor,
+                 counts: Sequence[int], n_units: int, group=None):
+    """gather_matches for rows that already sit in one arena (SceneMatcher.match_many:
+    arena_f32 [k, 5, cap] float32, arena_z [k, cap] float64, counts[i] rows of local unit i):
+    the padded [per_rank, n_max, 6] float64 block is built with a handful of batched
+    operations instead of several launches per unit.  Same collectives, same result.
+    -> (list of all n_units tables in unit order, this rank's own rows [N, 6])."""
+    world = dist.get_world_size(group)
+    dev = arena_f32.device
+    k = len(unit_ids)
+    counts_t = torch.zeros(n_units, dtype=torch.int64, device=dev)
+    if k:
+        counts_t[torch.as_tensor(list(unit_ids), dtype=torch.int64, device=dev)] = \
+            torch.as_tensor(list(counts), dtype=torch.int64, device=dev)
+    dist.all_reduce(counts_t, op=dist.ReduceOp.SUM, group=group)
+    per_rank = (n_units + world - 1) // world
+    cnt = counts_t.cpu().tolist()                                    # the one host synchronisation
+    n_max = max(max(cnt) if n_units else 0, 1)
+    mine = torch.zeros((per_rank, n_max, len(COLUMNS)), dtype=torch.float64, device=dev)
+    own = torch.zeros((0, len(COLUMNS)), dtype=torch.float64, device=dev)
+    if k:
+        w = min(n_max, arena_f32.shape[2])
+        mine[:k, :w, :5] = arena_f32[:k, :, :w].transpose(1, 2)      # float32 -> float64 is exact
+        mine[:k, :w, 5] = arena_z[:k, :w]
+        valid = torch.arange(n_max, device=dev)[None, :] < \
+            torch.as_tensor(list(counts), dtype=torch.int64, device=dev)[:, None]
+        mine[:k].masked_fill_(~valid[:, :, None], 0.0)               # stale arena rows (may hold NaN bits)
+        own = mine[:k][valid]
+    allr = torch.empty((world,) + tuple(mine.shape), dtype=torch.float64, device=dev)
+    dist.all_gather(list(allr.unbind(0)), mine, group=group)
+    return [allr[u % world, u // world, : cnt[u]] for u in range(n_units)], own
+
+
 def gather_moments(rows: torch.Tensor, group=None):
     """all_reduce of [n, sum dx, sum dy, sum dx^2, sum dy^2] and of the min / max
     of dx, dy -> dict with n, mean, std (population), min, max per component."""

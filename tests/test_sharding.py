@@ -30,7 +30,21 @@ def _worker(rank, world, port, n_units, out_dir):
         allrows = torch.cat(merged) if merged else torch.zeros((0, 6), dtype=torch.float64)
         mine = torch.cat(tables) if tables else torch.zeros((0, 6), dtype=torch.float64)
         mom = sharding.gather_moments(mine)
-        torch.save({"rows": allrows, "mom": mom, "ids": ids}, os.path.join(out_dir, f"r{rank}.pt"))
+        # the same exchange from a result arena (SceneMatcher.match_many layout): [k, 5, cap] float32
+        # columns + [k, cap] float64 zncc with stale (NaN) rows beyond each unit's count
+        cap = 16
+        a32 = torch.full((max(len(ids), 1), 5, cap), float("nan"), dtype=torch.float32)
+        az = torch.full((max(len(ids), 1), cap), float("nan"), dtype=torch.float64)
+        t32 = [t.to(torch.float32).to(torch.float64) for t in tables]       # what float32 columns can hold
+        for i, t in enumerate(tables):
+            a32[i, :, : t.shape[0]] = t[:, :5].t().to(torch.float32)
+            az[i, : t.shape[0]] = t[:, 5]
+        merged2, own2 = sharding.gather_units(ids, a32, az, [t.shape[0] for t in tables], n_units)
+        rows2 = torch.cat(merged2) if merged2 else torch.zeros((0, 6), dtype=torch.float64)
+        own_want = torch.cat([torch.cat([a[:, :5], b[:, 5:]], 1) for a, b in zip(t32, tables)]) if tables \
+            else torch.zeros((0, 6), dtype=torch.float64)
+        torch.save({"rows": allrows, "mom": mom, "ids": ids, "rows2": rows2,
+                    "own_ok": bool(torch.equal(own2, own_want))}, os.path.join(out_dir, f"r{rank}.pt"))
     finally:
         dist.destroy_process_group()
 
@@ -52,6 +66,8 @@ def test_gather_world2(tmp_path, n_units):
     for r in range(world):
         d = torch.load(os.path.join(tmp_path, f"r{r}.pt"))
         assert torch.equal(d["rows"], want)              # same table, unit order, on every rank
+        want2 = torch.cat([want[:, :5].to(torch.float32).to(torch.float64), want[:, 5:]], 1)
+        assert torch.equal(d["rows2"], want2) and d["own_ok"]      # arena exchange: same table
         seen += d["ids"]
         m = d["mom"]
         assert m["n"] == want.shape[0]
