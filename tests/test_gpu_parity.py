@@ -603,6 +603,59 @@ def test_sort_and_unlimited_corners(N):
     assert len(want) > 3 * 8192
 
 
+@pytest.mark.parametrize("case", [
+    # (h, w, dtype, ksize, tile_size, mask kind, nodata, maxCorners): widths with and without the
+    # 4-pixel Laplacian (w % 4), heights that are no multiple of the 64-row segments, 8/16-bit rasters,
+    # tiles with remainders, user mask, nodata value, zero blocks (auto mask)
+    (1100, 1500, "u16", 7, 20000, None, None, 3000),
+    (1047, 1302, "u16", 5, 20000, None, None, 2500),
+    (900, 1024, "u8", 7, 20000, None, None, 2000),
+    (1300, 1400, "u16", 7, 700, "user", None, 800),
+    (777, 1296, "i16", 3, 20000, None, None, 1500),
+    (1000, 1204, "u16", 7, 20000, "zeros", 1234, 2000),
+])
+def test_klt_match_shape_and_dtype_sweep(case):
+    """KLT.match + ZNCCService on mid-size synthetic pairs against the oracle (exact-integer LK
+    sums: corners identical incl. order, dx/dy bit-level close, ZNCC identical NaN pattern)."""
+    import pandas as pd
+    from karios_b200 import synth
+    from karios_b200.matcher.klt import KLT
+    from karios_b200.matcher.zncc_service import ZNCCService
+    from karios_b200.core.configuration import KLTConfiguration
+    from karios_b200.core.image import ArrayRaster
+    h, w, dt, ksize, tile, mask_kind, nodata, mc = case
+    ref_t, mon_t = synth.make_pair(h, w, seed=h + w, shift=(0.4, -0.3))
+    ref = ref_t.view(torch.int16).numpy().view(np.uint16).copy()
+    mon = mon_t.view(torch.int16).numpy().view(np.uint16).copy()
+    if dt == "u8":
+        ref, mon = (ref >> 4).astype(np.uint8), (mon >> 4).astype(np.uint8)
+    elif dt == "i16":
+        ref, mon = (ref.astype(np.int32) - 2500).astype(np.int16), (mon.astype(np.int32) - 2500).astype(np.int16)
+    mask = None
+    if mask_kind == "user":
+        mask = synth.make_mask(h, w, seed=3).numpy()
+    elif mask_kind == "zeros":
+        mon[200:330, 400:640] = 0
+        ref[:40, :300] = 0
+        mon[500:520, :] = nodata
+    kw = dict(laplacian_kernel_size=ksize, tile_size=tile, maxCorners=mc)
+    conf = KLTConfiguration(**kw)
+    mon_img, ref_img = ArrayRaster(mon, nodata), ArrayRaster(ref, nodata)
+    frames = list(KLT(conf).match(mon_img, ref_img, ArrayRaster(mask) if mask is not None else None))
+    want = O.match(mon, ref, mask, O.KLTConfiguration(**kw), nd_mon=nodata, nd_ref=nodata, acc_mode=1)
+    assert len(frames) == len(want) and len(frames) >= 1
+    for f, t in zip(frames, want):
+        assert np.array_equal(f["x0"].to_numpy(), t["x0"]) and np.array_equal(f["y0"].to_numpy(), t["y0"])
+        assert np.abs(f["dx"].to_numpy() - t["dx"]).max() < 1e-3
+        assert np.abs(f["dy"].to_numpy() - t["dy"]).max() < 1e-3
+    df = pd.concat(frames, ignore_index=True)
+    z = ZNCCService().compute_zncc(df, mon_img, ref_img).to_numpy()
+    zo = O.zncc(df["x0"].to_numpy(), df["y0"].to_numpy(), df["dx"].to_numpy(), df["dy"].to_numpy(), mon, ref)
+    assert np.array_equal(np.isnan(z), np.isnan(zo))
+    if (~np.isnan(zo)).any():
+        assert np.nanmax(np.abs(z - zo)) < 1e-5
+
+
 def test_full_s2_scene_properties_and_opencv():
     """BASELINE config 2: a full 10980 x 10980 pair through SceneMatcher (one tile,
     default config).  Size-independent properties, then -- when OpenCV is importable
