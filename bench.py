@@ -468,7 +468,7 @@ def cuda_arm(args):
             "cpu_baseline": cpu,
             "e2e": e2e,
             "next_rows": next_rows,
-            "pipeline": pipeline_diag, "exchange_ms": round(exchange_ms, 3), "gpu_launches": 28 * args.steps * len(sm.windows),      # own kernels per tile (profiles/ncu_launches_*.csv)
+            "pipeline": pipeline_diag, "exchange_ms": round(exchange_ms, 3), "gpu_launches": 27 * args.steps * len(sm.windows),      # own kernels per tile (profiles/ncu_launches_r1_v11.csv)
             "clocks": sampler.summary(),
             "stats_last": {k: v for k, v in st.as_dict().items() if k.startswith("n_") or k == "nms_rounds"},
         }
