@@ -237,6 +237,13 @@ def cuda_arm(args):
         _, wown = sharding.gather_units([rank + i * world for i in range(len(wtab))], sm.last_arena[0],
                                         sm.last_arena[1], sm.last_counts, world * len(wtab))
         sharding.gather_moments(wown)
+        # the exchange buffers of the timed batch (K units per rank) come from the caching
+        # allocator: have it hold blocks of that size before the timed region starts
+        cap_rows = sm.rows.capacity
+        warm_bufs = [torch.empty((world, args.steps, cap_rows, 6), dtype=torch.float64, device=dev),
+                     torch.empty((args.steps, cap_rows, 6), dtype=torch.float64, device=dev),
+                     torch.empty((args.steps * cap_rows, 6), dtype=torch.float64, device=dev)]
+        del warm_bufs
     del wtab
     torch.cuda.synchronize()
     if world > 1:
