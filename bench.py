@@ -245,6 +245,11 @@ def cuda_arm(args):
                      torch.empty((args.steps * cap_rows, 6), dtype=torch.float64, device=dev)]
         del warm_bufs
     del wtab
+    # the result arena of the timed call (K units) is larger than the warm-up's: let the caching
+    # allocator hold blocks of that size already (no cudaMalloc inside the timed region)
+    warm_arena = [torch.empty((args.steps, 5, sm.rows.capacity), dtype=torch.float32, device=dev),
+                  torch.empty((args.steps, sm.rows.capacity), dtype=torch.float64, device=dev)]
+    del warm_arena
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()

@@ -342,9 +342,10 @@ class Context:
         p = self.max_w * self.max_h
         return max(p // 8, 65536)
 
-    def pyr_down(self, u8):
+    def pyr_down(self, u8, out=None):
         h, w = u8.shape
-        out = torch.empty(((h + 1) // 2, (w + 1) // 2), dtype=torch.uint8, device=u8.device)
+        if out is None:
+            out = torch.empty(((h + 1) // 2, (w + 1) // 2), dtype=torch.uint8, device=u8.device)
         _check(self.lib.kr_pyr_down(self._h, u8.data_ptr(), _pitch(u8), w, h, out.data_ptr(),
                                     _pitch(out), _stream()))
         return out

@@ -136,6 +136,128 @@ __global__ void __launch_bounds__(PD_WARPS * 32) k_pyr_down(PyrPair pp, int w, i
     else pyr_down_body<false>(src, sp, dst, dp, w, h, dw, xs, oys, oye, lane);
 }
 
+// K5, four outputs per lane (w % 4 == 0, w >= 256, h >= 8, 4-byte aligned planes): a warp
+// covers 256 input columns / 120 output columns (lanes 1..30), a lane loads its 8 input bytes of
+// a row as two 32-bit words, the taps of the neighbour lanes arrive by two shuffles per row (for
+// four outputs), four dp4a form the horizontal sums, the vertical taps slide through registers
+// as packed 16-bit pairs, and the four results leave with one byte permute and one 32-bit store.
+// No scalar border path: the first warp starts 8 columns left of the image and its lane 0
+// mirrors lane 1's bytes (REFLECT_101), the last warp is shifted left to end at the image edge
+// and its lane 31 mirrors lane 30's; rows are reflected by index in the top / bottom blocks.
+constexpr int P4_VALID = 120, P4_ROWS = 32;
+
+struct P4Row { uint32_t lo, hi; };
+
+template <bool ROWFAST, bool EDGE>
+__device__ __forceinline__ void pyr4_body(const uint8_t *__restrict__ src, int64_t sp,
+                                          uint8_t *__restrict__ dst, int64_t dp, int h, int lc, int edge,
+                                          bool warp_edge, bool store_lane, bool lane31, int oc, int oys,
+                                          int oye)
+{
+    constexpr unsigned FULL = 0xffffffffu;
+    const int r0 = 2 * oys - 2;
+    const uint8_t *pl = src + (int64_t)r0 * sp + lc;               // ROWFAST
+    const uint8_t *pc = src + lc;
+    int r_load = r0;
+    auto load_next = [&]() -> P4Row {
+        const uint8_t *p;
+        if (ROWFAST) {
+            p = pl;
+            pl += sp;
+        } else {
+            int tr = r_load;
+            if (tr < 0) tr = -tr;
+            if (tr >= h) tr = 2 * (h - 1) - tr;
+            r_load++;
+            p = pc + (int64_t)tr * sp;
+        }
+        P4Row q;
+        q.lo = __ldg(reinterpret_cast<const uint32_t *>(p));
+        q.hi = (lane31 && edge == 0) ? 0u : __ldg(reinterpret_cast<const uint32_t *>(p + 4));
+        if (EDGE && warp_edge) {
+            if (edge == 1) q.hi = __byte_perm(q.lo, q.lo, 0x1200);       // columns -2, -1 = p2, p1
+            if (edge == 2) q.lo = __byte_perm(q.hi, q.hi, 0x3212);       // column w = p(w - 2)
+        }
+        return q;
+    };
+    // horizontal [1 4 6 4 1] sums of the lane's four outputs, packed (h0 | h1 << 16), (h2 | h3 << 16)
+    auto hsum = [&](const P4Row q, uint32_t &HA, uint32_t &HB) {
+        const uint32_t lw = __shfl_up_sync(FULL, q.hi, 1), rw = __shfl_down_sync(FULL, q.lo, 1);
+        const uint32_t w0 = __byte_perm(lw, q.lo, 0x5432);               // L.a6 L.a7 a0 a1
+        const uint32_t w2 = __byte_perm(q.lo, q.hi, 0x5432);             // a2 a3 a4 a5
+        const uint32_t h0 = __dp4a(w0, 0x04060401u, (q.lo >> 16) & 255u);
+        const uint32_t h1 = __dp4a(q.lo, 0x04060401u, q.hi & 255u);
+        const uint32_t h2 = __dp4a(w2, 0x04060401u, (q.hi >> 16) & 255u);
+        const uint32_t h3 = __dp4a(q.hi, 0x04060401u, rw & 255u);
+        HA = h0 | (h1 << 16);
+        HB = h2 | (h3 << 16);
+    };
+    uint8_t *po = dst + (int64_t)oys * dp + oc;
+    auto store_next = [&](uint32_t accA, uint32_t accB) {
+        const uint32_t wv = __byte_perm(accA, accB, 0x7531);             // (acc >> 8) & 255 of the four fields
+        if (store_lane) {
+            if (EDGE) {
+                *reinterpret_cast<uint16_t *>(po) = (uint16_t)wv;
+                *reinterpret_cast<uint16_t *>(po + 2) = (uint16_t)(wv >> 16);
+            } else {
+                *reinterpret_cast<uint32_t *>(po) = wv;
+            }
+        }
+        po += dp;
+    };
+    uint32_t a0, b0, a1, b1, a2, b2;
+    hsum(load_next(), a0, b0);
+    hsum(load_next(), a1, b1);
+    hsum(load_next(), a2, b2);
+    P4Row n0 = load_next(), n1 = load_next(), n2 = load_next(), n3 = load_next();
+    for (int oy = oys; oy < oye; oy += 2) {
+        const P4Row c0 = n0, c1 = n1, c2 = n2, c3 = n3;
+        if (oy + 2 < oye) { n0 = load_next(); n1 = load_next(); n2 = load_next(); n3 = load_next(); }
+        uint32_t a3, b3, a4, b4, a5, b5, a6, b6;
+        hsum(c0, a3, b3);
+        hsum(c1, a4, b4);
+        // packed 16-bit pairs: (h0 + h4) + 4 (h1 + h3) + 6 h2 + 128 <= 65408 per field
+        store_next(a0 + a4 + 4u * (a1 + a3) + 6u * a2 + 0x00800080u, b0 + b4 + 4u * (b1 + b3) + 6u * b2 + 0x00800080u);
+        hsum(c2, a5, b5);
+        hsum(c3, a6, b6);
+        if (oy + 1 < oye)
+            store_next(a2 + a6 + 4u * (a3 + a5) + 6u * a4 + 0x00800080u, b2 + b6 + 4u * (b3 + b5) + 6u * b4 + 0x00800080u);
+        a0 = a4; b0 = b4; a1 = a5; b1 = b5; a2 = a6; b2 = b6;
+    }
+}
+
+template <int PD_WARPS>
+__global__ void __launch_bounds__(PD_WARPS * 32) k_pyr_down4(PyrPair pp, int w, int h)
+{
+    const uint8_t *__restrict__ src = pp.src[blockIdx.z];
+    uint8_t *__restrict__ dst = pp.dst[blockIdx.z];
+    const int64_t sp = pp.src_pitch[blockIdx.z], dp = pp.dst_pitch[blockIdx.z];
+    const int dw = (w + 1) >> 1, dh = (h + 1) >> 1;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int nwx = (dw + P4_VALID - 1) / P4_VALID;
+    const int wx = min((int)blockIdx.x * PD_WARPS + wid, nwx - 1);   // spare warps recompute the last strip
+    int xs = wx * P4_VALID;
+    if (xs + P4_VALID > dw) xs = dw - P4_VALID;                      // last warp: shifted left, outputs overlap
+    const int c0 = 2 * xs - 8;                                       // first (virtual) input column of the warp
+    // right: lane 31's first column is the first one past the image (only the shifted last warp);
+    // otherwise lane 31 supplies one true pixel (its byte 0) and never touches its upper word,
+    // which may lie past the end of the row
+    const bool left = c0 < 0, right = c0 + 248 >= w;
+    int lc = c0 + 8 * lane, edge = 0;
+    if (left && lane == 0) { lc = 0; edge = 1; }
+    if (right && lane == 31) { lc = c0 + 8 * 30; edge = 2; }
+    const bool store_lane = lane >= 1 && lane <= 30;
+    const int oc = xs + 4 * (lane - 1);
+    const int oys = blockIdx.y * P4_ROWS, oye = min(oys + P4_ROWS, dh);
+    const bool rowfast = (2 * oys - 2 >= 0) && (2 * oye + 6 <= h);
+    const bool edge_block = blockIdx.x == 0 || blockIdx.x == gridDim.x - 1;      // block-uniform
+#define P4_BODY(RF, ED) \
+    pyr4_body<RF, ED>(src, sp, dst, dp, h, lc, edge, left || right, store_lane, lane == 31, oc, oys, oye)
+    if (edge_block) { if (rowfast) P4_BODY(true, true); else P4_BODY(false, true); }
+    else { if (rowfast) P4_BODY(true, false); else P4_BODY(false, false); }
+#undef P4_BODY
+}
+
 // warps per block of k_pyr_down: few, so that the blocks holding an image edge (general path
 // for all their warps) stay a small share; KR_PYR_WARPS overrides (1, 2, 4, 8)
 int pyr_warps()
@@ -151,6 +273,23 @@ int pyr_warps()
 int launch_pyr_down(const PyrPair &q, int w, int h, int nw, int nh, int nz, int aligned, cudaStream_t s)
 {
     const int pw = pyr_warps();
+    static const bool no4 = getenv("KR_NO_PYR4") != nullptr;
+    bool ok4 = !no4 && w % 4 == 0 && w >= 256 && h >= 8;
+    for (int k = 0; k < nz; k++)
+        ok4 = ok4 && ((uintptr_t)q.src[k] % 4 == 0) && (q.src_pitch[k] % 4 == 0) && ((uintptr_t)q.dst[k] % 4 == 0) &&
+              (q.dst_pitch[k] % 4 == 0);
+    if (ok4) {
+        const int nwx = (nw + P4_VALID - 1) / P4_VALID;
+        dim3 g4((nwx + pw - 1) / pw, (nh + P4_ROWS - 1) / P4_ROWS, nz);
+        switch (pw) {
+        case 1: k_pyr_down4<1><<<g4, 32, 0, s>>>(q, w, h); break;
+        case 4: k_pyr_down4<4><<<g4, 128, 0, s>>>(q, w, h); break;
+        case 8: k_pyr_down4<8><<<g4, 256, 0, s>>>(q, w, h); break;
+        default: k_pyr_down4<2><<<g4, 64, 0, s>>>(q, w, h); break;
+        }
+        KR_LAUNCH_CHECK();
+        return KR_OK;
+    }
     dim3 grid((nw + pw * PD_VALID - 1) / (pw * PD_VALID), (nh + PD_ROWS - 1) / PD_ROWS, nz);
     switch (pw) {
     case 1: k_pyr_down<1><<<grid, 32, 0, s>>>(q, w, h, aligned); break;

@@ -233,9 +233,29 @@ def test_corner_modes_agree(golden, N):
 def test_pyr_down(golden, N, ctx, name):
     g = golden(name)
     assert np.array_equal(ctx.pyr_down(dev(g["lap_ref"])).cpu().numpy(), g["pyr_ref"])
-    for shape in ((1, 1), (2, 2), (7, 9), (51, 50), (130, 257)):
+    # the last shapes take the 4-outputs-per-lane kernel (w % 4 == 0, w >= 256): mirrored first /
+    # last lanes, shifted last warp, odd heights, reflected top / bottom rows, pitched windows
+    for shape in ((1, 1), (2, 2), (7, 9), (51, 50), (130, 257), (8, 256), (37, 260), (64, 492), (131, 1000),
+                  (301, 724), (66, 1024)):
         a = np.random.default_rng(1).integers(0, 255, shape).astype(np.uint8)
         assert np.array_equal(ctx.pyr_down(dev(a)).cpu().numpy(), O.pyr_down(a)), shape
+    # output planes with an aligned pitch (as the context's pyramid planes have): the 4-output kernel
+    # for widths whose last full warp ends a few columns before the image edge
+    for shape in ((21, 1204), (19, 1208), (33, 964), (18, 1212), (40, 260), (9, 10980)):
+        a = np.random.default_rng(3).integers(0, 255, shape).astype(np.uint8)
+        dh_, dw_ = (shape[0] + 1) // 2, (shape[1] + 1) // 2
+        buf = torch.zeros((dh_, (dw_ + 127) // 128 * 128), dtype=torch.uint8, device="cuda")
+        got = ctx.pyr_down(dev(a), out=buf[:, :dw_]).cpu().numpy() if shape[1] <= 1024 else None
+        if got is None:
+            c2 = N.Context(shape[1], max(shape[0], 16), 100)
+            got = c2.pyr_down(dev(a), out=buf[:, :dw_]).cpu().numpy()
+            c2.close()
+        assert np.array_equal(got, O.pyr_down(a)), shape
+    big = np.random.default_rng(2).integers(0, 255, (300, 1024)).astype(np.uint8)
+    t = dev(big)
+    for (y, x, h, w) in ((0, 0, 300, 1024), (10, 256, 200, 512), (3, 4, 257, 1016)):
+        got = ctx.pyr_down(t[y:y + h, x:x + w]).cpu().numpy()
+        assert np.array_equal(got, O.pyr_down(big[y:y + h, x:x + w])), (y, x, h, w)
 
 
 @pytest.mark.parametrize("name", CASES)
