@@ -403,6 +403,31 @@ def cuda_arm(args):
     except Exception as e:  # noqa: BLE001
         next_rows["scene_passes"] = {"error": repr(e)}
 
+    # ---- automatic kernel-size search on the full scene -----------
+    try:
+        if args.quick:
+            raise RuntimeError("skipped (--quick)")
+        from karios_b200.core.image import DeviceRaster
+        from karios_b200.matcher.klt import KLT
+        mon, ref = scenes[0]
+        aconf = default_conf(KLTConfiguration, laplacian_kernel_size="auto")
+        res = {}
+        for label, batched in (("device_search", True), ("host_loop", False)):
+            k = KLT(aconf)
+            k._batched_auto = batched
+            list(k.match(DeviceRaster(mon), DeviceRaster(ref), None))          # warm-up (context, scratch)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            frames = list(k.match(DeviceRaster(mon), DeviceRaster(ref), None))
+            torch.cuda.synchronize()
+            res[label] = {"ms": round(1e3 * (time.perf_counter() - t0), 2), "rows": int(sum(len(f) for f in frames)),
+                          "selected": list(k.auto_selected_ksize or ())}
+        next_rows["auto_ksize"] = {
+            "what": "KLT.match with laplacian_kernel_size='auto': 5+5 Laplacians, 5 corner sets, 25 LK round trips "
+                    "(kr_auto_ksize: one launch sequence, one sync) vs one kr_klt_track per pair", **res}
+    except Exception as e:  # noqa: BLE001
+        next_rows["auto_ksize"] = {"error": repr(e)}
+
     # ---- end to end: pinned host rasters -> rows on the host -----------------
     e2e = None
     if not args.no_e2e:

@@ -2,6 +2,7 @@
 #include <stdarg.h>
 #include <stdio.h>
 #include <string.h>
+#include <stdlib.h>
 #include <math.h>
 #include <new>
 #include "kr_internal.cuh"
@@ -245,7 +246,10 @@ KR_API int kr_ctx_create(int device, int max_w, int max_h, int max_corners, kr_c
         int bps = 0;
         rc = kr_nms_occupancy(&bps);
         if (rc == KR_OK && bps < 1) rc = kr_set_error(KR_ERR_CUDA, "NMS kernel does not fit on an SM");
-        c->nms_grid = c->num_sms * (bps > 2 ? 2 : bps);
+        // blocks per SM of the persistent NMS grid (KR_NMS_BPS = 1 | 2; default 2)
+        const char *nb = getenv("KR_NMS_BPS");
+        const int want = (nb && atoi(nb) == 1) ? 1 : 2;
+        c->nms_grid = c->num_sms * (bps > want ? want : bps);
     }
     if (rc == KR_OK) rc = krl_reset_stats(c, 0);
     if (rc == KR_OK) {
