@@ -765,11 +765,12 @@ int launch_lap4(kr_ctx *ctx, const void *img, int64_t pitch, int w, int h, int s
     KR_CUDA(cfg.err);
     const int bps = cfg.bps, seg_env = cfg.seg;
     const int nwx = (w + L4_VALID - 1) / L4_VALID, bx = (nwx + L4_WARPS - 1) / L4_WARPS;
-    // 64-row segments: several waves of blocks in different phases (load / cascade / store)
-    // balance better than one wave of long segments (measured: 0.121 vs 0.175 ms per S2 plane),
-    // for 2R / 64 extra warm-up rows; small images get at least one block per SM slot
+    // 96-row segments: several waves of blocks in different phases (load / cascade / store)
+    // balance better than one wave of long segments (measured per S2 plane: 0.175 ms at 244
+    // rows, 0.144 at 128, 0.120 at 96, 0.124 at 64, 0.135 at 32), for 2R / 96 extra warm-up rows;
+    // small images get at least one block per SM slot
     (void)bps;
-    int seg = seg_env > 0 ? ((seg_env + 3) & ~3) : 64;
+    int seg = seg_env > 0 ? ((seg_env + 3) & ~3) : 96;
     if (seg_env <= 0) {
         const int slots = ctx->num_sms * bps;
         while (seg > 32 && (int64_t)bx * ((h + seg - 1) / seg) < slots) seg -= 16;
