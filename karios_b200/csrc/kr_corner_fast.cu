@@ -268,6 +268,43 @@ __device__ __forceinline__ void approx_body(
             pushed_l = fmaxf(wl_, pushed_l);
             run_l = fmaxf(wl_, kr_f32_dec_bits(genc, 0));
         }
+        if constexpr (STEADY && !BORDER) {
+            // Steady interior rows: Q.U is NaN on the halo lanes and every row / column is inside the
+            // image, so rl[] already marks exactly this warp's possible candidates.  The first one of
+            // each lane is chosen without branches; further ones in the same lane (bounds of
+            // neighbouring pixels overlap) take the per-column ballots below.
+            const bool r0 = rl[0], r1 = rl[1], r2 = rl[2], r3 = rl[3];
+            const bool any_l = r0 || r1 || r2 || r3;
+            const unsigned cb = __ballot_sync(FULL, any_l);
+            if (cb == 0) return;
+            if (ccount > FA_CBUF - 128) {                   // flush the warp buffer
+                uint32_t base = 0;
+                if (lane == 0) base = atomicAdd(&st->n_cand, (uint32_t)ccount);
+                base = __shfl_sync(FULL, base, 0);
+                __syncwarp();
+                for (int k = lane; k < ccount; k += 32) {
+                    if (base + k < cand_cap) cand[base + k] = cbuf[k]; else st->overflow = 1;
+                }
+                __syncwarp();
+                ccount = 0;
+            }
+            const uint32_t idx0 = (uint32_t)(m * w + xb);
+            const float u = r0 ? Q.U[0] : r1 ? Q.U[1] : r2 ? Q.U[2] : Q.U[3];
+            const uint32_t jj = r0 ? 0u : r1 ? 1u : r2 ? 2u : 3u;
+            if (any_l) cbuf[ccount + __popc(cb & lt_mask)] = ((uint64_t)__float_as_uint(u) << 32) | (idx0 + jj);
+            ccount += __popc(cb);
+            const bool more[3] = {r1 && r0, r2 && (r0 || r1), r3 && (r0 || r1 || r2)};
+            if (__any_sync(FULL, more[0] || more[1] || more[2])) {
+#pragma unroll
+                for (int j = 1; j < 4; j++) {
+                    const unsigned bal = __ballot_sync(FULL, more[j - 1]);
+                    if (more[j - 1])
+                        cbuf[ccount + __popc(bal & lt_mask)] = ((uint64_t)__float_as_uint(Q.U[j]) << 32) | (idx0 + j);
+                    ccount += __popc(bal);
+                }
+            }
+            return;
+        }
         const unsigned any_b = __ballot_sync(FULL, rl[0] || rl[1] || rl[2] || rl[3]);
         if (any_b == 0) return;
         unsigned cm = 0, lm = 0;
