@@ -3,11 +3,12 @@
 shaped scene pairs (BASELINE.json: matches/s and scene-pairs/s, HBM roofline).
 
     python bench.py --gpus N --steps K --warmup W          # CUDA arm
-    python bench.py --impl reference --steps K --warmup W   # OpenCV CPU arm
+    python bench.py --impl reference --steps K --warmup W   # the unmodified reference on the host CPUs
 
 One step = one 10980 x 10980 uint16 scene pair through the whole path (auto mask,
 min/max, uint8 + Laplacian k7 of both rasters, Shi-Tomasi corners, pyramidal LK
-forward + backward, back-check, (x0,y0) sort, ZNCC), default KARIOS config.
+forward + backward, back-check, (x0,y0) sort, ZNCC of the rows with score >= 0.4),
+default KARIOS config.  Both arms run this same workload (same `config`).
 Prints ONE JSON line on rank 0.
 """
 from __future__ import annotations
@@ -39,8 +40,13 @@ def parse():
     ap.add_argument("--scenes", type=int, default=2, help="distinct synthetic scenes per rank")
     ap.add_argument("--depth", type=int, default=4,
                     help="scene pairs in flight per GPU (independent contexts + streams)")
+    ap.add_argument("--batches", type=int, default=5,
+                    help="the K-step timed batch is repeated this many times; the median batch is reported")
+    ap.add_argument("--ref-budget", type=float, default=float(os.environ.get("KR_REF_BUDGET_S", "150")),
+                    help="--impl reference: stop timing further full-scene steps after this many seconds")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-numa", action="store_true", help="do not bind the rank to its GPU's NUMA node")
     ap.add_argument("--quick", action="store_true",
                     help="tuning runs: resident throughput and stage times only (no e2e, CPU or next-row legs)")
     a = ap.parse_args()
@@ -58,8 +64,21 @@ def default_conf(cls, **kw):
     return cls(**base)
 
 
+def bench_config(size, world):
+    """The workload both arms run (the driver compares the two `config` objects)."""
+    return {"workload": WORKLOAD if size == S2 else f"synthetic_{size}x{size}_pair_klt_zncc",
+            "scene": f"{size}x{size} uint16 pair, synthetic texture (karios_b200/synth.py, seed 1234 + scene index), "
+                     "monitored shifted by (+0.30,-0.20) px",
+            "klt": "maxCorners 20000, minDistance 10, blocksize 15, winsize 25, q 0.1, k7, tile_size 20000 (1 tile)",
+            "scoring": "ZNCC of the rows with KLT score >= 0.4",
+            "parallelism": f"scene pairs sharded over {world} GPU(s), no data-path collective",
+            "l2": "inputs (482 MB per pair) exceed the 126 MB L2; no flush needed"}
+
+
 # ------------------------------------------------------------------ CPU legs
-def cpu_scene_host(size, seed):
+def scene_host(size, seed):
+    """Scene `seed` as host uint16 arrays (generated on the GPU when there is one: the
+    torch generator is bit-identical on both, and minutes faster there)."""
     import torch
     from karios_b200 import synth
     dev = "cuda" if torch.cuda.is_available() else "cpu"
@@ -68,64 +87,56 @@ def cpu_scene_host(size, seed):
     return to_np(ref), to_np(mon)
 
 
-def cpu_run(ref, mon, conf):
-    """One pass of the reference CPU path over (ref, mon): OpenCV when importable
-    (the routines the reference itself calls), else the C restatement."""
-    from oracle import cv2_path as P
-    from oracle import oracle as O
-    if P.HAVE_CV2:
-        import cv2
-        cv2.setNumThreads(os.cpu_count() or 1)
-        t0 = time.perf_counter()
-        _, total = P.match_scene(mon, ref, None, conf)
-        return total, time.perf_counter() - t0, "opencv-%s + numpy (oracle/cv2_path.py)" % cv2.__version__
-    t0 = time.perf_counter()
-    tiles = O.match(mon, ref, None, conf)
-    total = 0
-    for t in tiles:
-        sel = t["score"] >= np.float32(0.4)
-        O.zncc(t["x0"][sel], t["y0"][sel], t["dx"][sel], t["dy"][sel], mon, ref)
-        total += len(t["x0"])
-    return total, time.perf_counter() - t0, "oracle/klt_oracle.c (OpenMP)"
-
-
-def cpu_sample_conf(size, frac_side):
-    """A crop of side size/frac_side with maxCorners scaled by the area, so that
-    matches per second stays comparable with the full scene."""
-    from oracle import oracle as O
-    side = max(256, size // frac_side)
-    mc = max(200, int(round(20000 * (side / float(S2)) ** 2)))
-    return side, default_conf(O.KLTConfiguration, maxCorners=mc)
+def reference_pass(ref, mon):
+    """One pass of the UNMODIFIED reference over (ref, mon): KLT.match + compute_zncc from
+    oracle/_ref (placed by build(); see oracle/vendor_ref.py, oracle/ref_run.py)."""
+    import logging
+    from oracle import ref_run, refimport
+    refimport.use_vendored()
+    logging.getLogger("karios").setLevel(logging.ERROR)      # one warning per border row otherwise
+    df, secs, how = ref_run.run_pair(mon, ref, None, threshold=0.4)
+    return len(df), secs, how
 
 
 def reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    # bounded sample: quarter scene (side/2); shrink when many steps are requested
-    frac = 2
-    if (args.steps + args.warmup) > 40:
-        frac = 4
-    side, conf = cpu_sample_conf(args.size, frac)
-    ref, mon = cpu_scene_host(side, 1234)
+    world = int(os.environ.get("WORLD_SIZE", str(args.gpus)))
+    size = args.size
+    ref, mon = scene_host(size, 1234)
     how = ""
-    for _ in range(args.warmup):
-        _, _, how = cpu_run(ref, mon, conf)
-    matches, secs = 0, 0.0
+    t_all = time.perf_counter()
+    # the CPU path has no compilation or caches to warm beyond the first pass: one warm-up
+    # pass of the full scene, whatever W is (stated in the line)
+    warm = min(1, args.warmup)
+    for _ in range(warm):
+        _, _, how = reference_pass(ref, mon)
+    matches, secs, done = 0, 0.0, 0
+    per_step = []
     for _ in range(args.steps):
-        m, s, how = cpu_run(ref, mon, conf)
+        m, s, how = reference_pass(ref, mon)
         matches += m
         secs += s
+        per_step.append(round(s, 3))
+        done += 1
+        if time.perf_counter() - t_all > args.ref_budget and done >= 3:
+            break
     value = matches / secs if secs > 0 else 0.0
-    sample = f"{side}x{side} crop of the scene, maxCorners {conf.maxCorners} (area-scaled), {how}"
+    cores = os.cpu_count()
+    sample = (f"{done} full {size}x{size} scene pairs timed (of {args.steps} requested: full-scene passes stop "
+              f"after {args.ref_budget:.0f} s), {warm} warm-up pass; {how}; cv2.setNumThreads({cores})")
     line = {
         "impl": "reference", "metric": "matches_per_sec", "value": value, "unit": "matches/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": 1e3 * secs / max(1, args.steps), "higher_is_better": True, "scaling": "weak",
+        "steps_timed": done, "warmup_run": warm,
+        "ms_per_step": 1e3 * secs / max(1, done), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "sample": sample},
-        "scene_pairs_per_sec": (value / 20000.0),
-        "cpu_baseline": {"value": value, "unit": "matches/s", "cores": os.cpu_count(), "kind": "port",
+        "config": bench_config(size, world),
+        "scene_pairs_per_sec": done / secs if secs > 0 else 0.0,
+        "matches_per_scene": matches / max(1, done),
+        "seconds_per_step": per_step,
+        "cpu_baseline": {"value": value, "unit": "matches/s", "cores": cores, "kind": "reference",
                          "sample": sample},
         "e2e": {"value": value, "unit": "matches/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -138,6 +149,7 @@ class ClockSampler(threading.Thread):
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index, self.stop_flag, self.samples, self.reasons = index, threading.Event(), [], set()
+        self.active = threading.Event()
         self.max_mhz = None
         try:
             import pynvml
@@ -157,15 +169,16 @@ class ClockSampler(threading.Thread):
                  "sw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
                  "sw_power_cap": getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4)}
         while not self.stop_flag.is_set():
-            try:
-                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
-                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
-                for k, bit in names.items():
-                    if r & bit:
-                        self.reasons.add(k)
-            except Exception:  # noqa: BLE001
-                pass
-            time.sleep(0.02)
+            if self.active.is_set():            # only while a timed batch is running
+                try:
+                    self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                    for k, bit in names.items():
+                        if r & bit:
+                            self.reasons.add(k)
+                except Exception:  # noqa: BLE001
+                    pass
+            time.sleep(0.003)
 
     def summary(self):
         med = float(np.median(self.samples)) if self.samples else None
@@ -194,7 +207,33 @@ def stage_bytes(P, C, n_corners, n_z):
     }
 
 
+def _max_over_ranks(dist, dev, world, *vals):
+    import torch
+    if world == 1:
+        return vals
+    t = torch.tensor(list(vals), device=dev, dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return tuple(float(v) for v in t)
+
+
+def _sum_over_ranks(dist, dev, world, *vals):
+    import torch
+    if world == 1:
+        return vals
+    t = torch.tensor(list(vals), device=dev, dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return tuple(float(v) for v in t)
+
+
 def cuda_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    from karios_b200 import sharding
+    numa = {"bound": False, "skipped": True}
+    if not args.no_numa:
+        numa = sharding.bind_to_gpu_numa(local)       # before any pinned allocation
+
     import torch
     import torch.distributed as dist
     from karios_b200 import _native as N
@@ -202,9 +241,6 @@ def cuda_arm(args):
     from karios_b200.api import SceneMatcher, ScenePipeline
     from karios_b200.core.configuration import KLTConfiguration
 
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
@@ -218,6 +254,7 @@ def cuda_arm(args):
         pass
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
+    lib = N.load_library()
 
     # scenes resident in HBM: scene i of this rank has seed 1234 + rank + i * world
     scenes = []
@@ -227,80 +264,78 @@ def cuda_arm(args):
     torch.cuda.synchronize()
     sm = SceneMatcher(size, size, conf, 0.4, device=dev, depth=args.depth)
     sm.trace_units = bool(os.environ.get("KR_TRACE_UNITS"))
+    cap = sm.rows.capacity
+    side = torch.cuda.Stream(device=dev)
 
-    from karios_b200 import sharding
+    def batch(n_pairs):
+        """n_pairs scene pairs of this rank (+ the exchange when sharded) -> (rows of this rank, gathered)"""
+        seq = [scenes[i % len(scenes)] for i in range(n_pairs)]
+        if world > 1:
+            g, tot = sharding.match_many_exchange(sm, seq, None, side)
+            m = sharding.batch_moments(g)          # statistics of the whole batch, on the device
+            return tot, (g, m)
+        _, tot = sm.match_many(seq)
+        return tot, None
 
     sampler = ClockSampler(local)          # NVML is initialised before the timed region
-    wtab, _ = sm.match_many([scenes[i % len(scenes)] for i in range(args.warmup)])
-    if world > 1:
-        # warm-up of the exchange step too (NCCL sets its channels up on the first collective)
-        _, wown = sharding.gather_units([rank + i * world for i in range(len(wtab))], sm.last_arena[0],
-                                        sm.last_arena[1], sm.last_counts, world * len(wtab))
-        sharding.gather_moments(wown)
-        # the exchange buffers of the timed batch (K units per rank) come from the caching
-        # allocator: have it hold blocks of that size before the timed region starts
-        cap_rows = sm.rows.capacity
-        warm_bufs = [torch.empty((world, args.steps, cap_rows, 6), dtype=torch.float64, device=dev),
-                     torch.empty((args.steps, cap_rows, 6), dtype=torch.float64, device=dev),
-                     torch.empty((args.steps * cap_rows, 6), dtype=torch.float64, device=dev)]
-        del warm_bufs
-    del wtab
-    # the result arena of the timed call (K units) is larger than the warm-up's: let the caching
-    # allocator hold blocks of that size already (no cudaMalloc inside the timed region)
-    warm_arena = [torch.empty((args.steps, 5, sm.rows.capacity), dtype=torch.float32, device=dev),
-                  torch.empty((args.steps, sm.rows.capacity), dtype=torch.float64, device=dev)]
-    del warm_arena
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
     sampler.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    # warm-up: W steps, then one untimed batch of the timed size (the caching allocator then holds
+    # the arena / gather blocks of that size: no cudaMalloc inside a timed batch; NCCL channels up)
+    batch(max(args.warmup, 1))
+    batch(args.steps)
     torch.cuda.synchronize()
-    e0.record()
-    # K steps = K scene pairs, `depth` of them in flight (each on its own context
-    # and stream); every pair's rows are collected
-    tables, matches = sm.match_many([scenes[i % len(scenes)] for i in range(args.steps)])
-    e_mid = torch.cuda.Event(enable_timing=True)
-    e_mid.record()
-    if world > 1:
-        # the one exchange step of the path: every rank ends with the match tables of
-        # all world*steps scene pairs (all_reduce of counts + NCCL all_gather of rows)
-        # and the global dx/dy moments
-        n_units = world * args.steps
-        ids = [rank + i * world for i in range(args.steps)]
-        merged, own = sharding.gather_units(ids, sm.last_arena[0], sm.last_arena[1], sm.last_counts, n_units)
-        sharding.gather_moments(own)
-        assert len(merged) == n_units
-    e1.record()
-    torch.cuda.synchronize()
+
+    batches = []
+    launches = None
+    diag = None
+    for b in range(max(1, args.batches)):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = int(lib.kr_launch_count())
+        sampler.active.set()
+        e0.record()
+        # K steps = K scene pairs, `depth` of them in flight (each on its own context and stream);
+        # sharded runs end with the one exchange step of the path (all_gather of the fixed-size
+        # unit records, issued on a side stream when the last unit is enqueued)
+        tot, gathered = batch(args.steps)
+        e1.record()
+        torch.cuda.synchronize()
+        sampler.active.clear()
+        launches = int(lib.kr_launch_count()) - l0
+        ms_b = e0.elapsed_time(e1)
+        if world > 1:
+            dist.barrier()
+        (ms_b,) = _max_over_ranks(dist, dev, world, ms_b)
+        (tot_all,) = _sum_over_ranks(dist, dev, world, float(tot))
+        done_t = list(getattr(sm, "unit_done_t", []))
+        gaps = [y - x for x, y in zip(done_t, done_t[1:])]
+        batches.append({"ms": ms_b, "matches": int(tot_all), "redo_units": int(getattr(sm, "n_redo", 0)),
+                        "max_unit_gap_ms": round(1e3 * max(gaps), 3) if gaps else None})
+        if world > 1 and b == 0:
+            assert gathered[0].shape[0] == world and gathered[0].shape[1] == args.steps
+            diag = sharding.moments_dict(gathered[1])
     sampler.stop_flag.set()
-    # host-side view of the timed region: exact re-runs (select_incomplete) and the largest gap
-    # between two finished units (a stalled host thread or device shows up here)
-    if getattr(sm, "unit_events", None):
-        ev = sm.unit_events
-        base = ev[0][0]
-        tl = [(round(base.elapsed_time(a), 3), round(base.elapsed_time(b), 3), round(1e3 * (t1 - t0), 3)) for a, b, t0, t1 in ev]
-        h0 = ev[0][2]
-        print("UNIT TIMELINE (gpu start ms, gpu end ms, host enqueue ms, host t ms):", file=sys.stderr)
-        for (a, b, q), e in zip(tl, ev):
-            print(f"  {a:9.3f} {b:9.3f} dur {b - a:8.3f}  enq {q:7.3f}  host_t {1e3 * (e[2] - h0):9.3f}", file=sys.stderr)
-    done_t = list(getattr(sm, "unit_done_t", []))
-    gaps = [b - a for a, b in zip(done_t, done_t[1:])]
-    pipeline_diag = {"redo_units": int(getattr(sm, "n_redo", 0)), "redo_flags": list(getattr(sm, "redo_flags", []))[:4],
-                     "max_unit_gap_ms": round(1e3 * max(gaps), 3) if gaps else None,
-                     "median_unit_gap_ms": round(1e3 * float(np.median(gaps)), 3) if gaps else None}
-    ms = e0.elapsed_time(e1)
-    exchange_ms = e_mid.elapsed_time(e1) if world > 1 else 0.0
-    if world > 1:
-        dist.barrier()
-        t = torch.tensor([ms, float(matches)], device=dev, dtype=torch.float64)
-        tmax = t.clone()
-        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        ms, matches = float(tmax[0]), int(t[1])
+    order = sorted(range(len(batches)), key=lambda i: batches[i]["ms"])
+    med = batches[order[len(order) // 2]]
+    ms, matches = med["ms"], med["matches"]
     secs = ms / 1e3
     value = matches / secs
     pairs_per_sec = world * args.steps / secs
+
+    # exchange alone (sharded runs): the collective on an idle device, for the record
+    exchange_ms = 0.0
+    if world > 1:
+        torch.cuda.synchronize()
+        dist.barrier()
+        a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        g = sharding.exchange(sm.last_arena)
+        sharding.batch_moments(g)
+        b_.record()
+        torch.cuda.synchronize()
+        (exchange_ms,) = _max_over_ranks(dist, dev, world, a.elapsed_time(b_))
 
     # ---- per-stage device times (CUDA events on the launching stream) --------
     sm.ctx.set_profiling(True)
@@ -313,6 +348,13 @@ def cuda_arm(args):
         for k, v in sm.ctx.stage_ms().items():
             acc[k] = acc.get(k, 0.0) + v / reps
     sm.ctx.set_profiling(False)
+    # one pair alone, no other pair in flight (latency of the path)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for i in range(5):
+        sm.ctx.match_tile(*scenes[i % len(scenes)], None, sm.windows[0], sm.kconf, sm.rows)
+    torch.cuda.synchronize()
+    single_pair_ms = 1e3 * (time.perf_counter() - t0) / 5
     P = size * size
     n_z = int((sm.rows.f32[4, : st.n_kept] >= 0.4).sum().item())
     sb = stage_bytes(P, st.n_candidates, st.n_corners, n_z)
@@ -400,6 +442,25 @@ def cuda_arm(args):
         ms_cv, nvalid = timed(lambda: kapi.count_valid_pixels(DeviceRaster(mon)))
         next_rows["count_valid"] = {"ms": round(ms_cv, 4), "value": int(nvalid), "alg_bytes": P * 2,
                                     "gbs": round(P * 2 / (ms_cv * 1e6), 1), "bound": "hbm"}
+        # config 4 (--enable-large-shift-detection) on the full scene: monitored shifted by whole
+        # pixels (+37 columns, -52 rows), detection, shift_image, KLT on the shifted raster
+        mon_far = N.shift_image(mon, 52, -37)
+
+        def cfg4():
+            return kapi.match_pair_large_shift(mon_far, ref, None, conf, offset_threshold=10)
+        cfg4()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        df4, applied = cfg4()
+        torch.cuda.synchronize()
+        next_rows["config4_large_shift"] = {
+            "what": "match_images with enable_large_shift_detection on the full scene, monitored displaced by "
+                    "(+37, -52) px: phase correlation, shift_image, KLT on the shifted raster, offsets added back",
+            "ms": round(1e3 * (time.perf_counter() - t0), 2), "applied_offset_xy": [float(v) for v in applied]
+            if applied else None, "rows": int(len(df4)), "mean_dx": float(df4.dx.mean()),
+            "mean_dy": float(df4.dy.mean()),
+            "fft_peak_mem_gb": round(torch.cuda.max_memory_allocated() / 2 ** 30, 2)}
+        del mon_far, df4
     except Exception as e:  # noqa: BLE001
         next_rows["scene_passes"] = {"error": repr(e)}
 
@@ -428,41 +489,105 @@ def cuda_arm(args):
     except Exception as e:  # noqa: BLE001
         next_rows["auto_ksize"] = {"error": repr(e)}
 
-    # ---- end to end: pinned host rasters -> rows on the host -----------------
-    e2e = None
+    # ---- end to end: host rasters -> rows on the host ------------------------------
+    e2e, e2e_dropin, h2d = None, None, None
     if not args.no_e2e:
-        pipe = ScenePipeline(size, size, torch.uint16, conf, 0.4, device=dev)
+        n_e2e = max(args.steps, 1)
         host_pairs = [(m.cpu().pin_memory(), r.cpu().pin_memory()) for m, r in scenes]
-        seq = [host_pairs[i % len(host_pairs)] for i in range(max(args.steps, 1))]
-        pipe.run(seq[: max(1, min(args.warmup, 2))])
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        t0 = time.perf_counter()
-        m2 = pipe.run(seq)
-        torch.cuda.synchronize()
-        dt = time.perf_counter() - t0
-        if world > 1:
-            t = torch.tensor([dt, float(m2)], device=dev, dtype=torch.float64)
-            tmax = t.clone()
-            dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-            dist.all_reduce(t, op=dist.ReduceOp.SUM)
-            dt, m2 = float(tmax[0]), int(t[1])
-        e2e = {"value": m2 / dt, "unit": "matches/s", "h2d_bytes_per_step": 2 * P * 2,
-               "d2h_bytes_per_step": int(st.n_kept) * (5 * 4 + 8),
-               "scene_pairs_per_sec": world * len(seq) / dt, "ms_per_step": 1e3 * dt / len(seq)}
-        pipe.close()
+        seq = [host_pairs[i % len(host_pairs)] for i in range(n_e2e)]
+        bytes_pair = 2 * P * 2
 
-    # ---- CPU baseline beside it (rank 0, N = 1 only) --------------------------
+        def wall(fn):
+            torch.cuda.synchronize()
+            if world > 1:
+                dist.barrier()
+            t0 = time.perf_counter()
+            out = fn()
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+            (dt,) = _max_over_ranks(dist, dev, world, dt)
+            return dt, out
+
+        # (0) the copy ceiling: the same pinned rasters, the same double-buffered H2D copies,
+        #     no kernel at all -- what the host side of this box can deliver to N GPUs at once
+        pipe = ScenePipeline(size, size, torch.uint16, conf, 0.4, device=dev)
+        pipe.copy_only(seq[:2])
+        dt_copy, _ = wall(lambda: pipe.copy_only(seq))
+        h2d = {"what": "copy-only run of the e2e leg: same pinned rasters and buffers, no kernels",
+               "scene_pairs_per_sec": world * len(seq) / dt_copy, "gbs_per_gpu": bytes_pair * len(seq) / dt_copy / 1e9,
+               "gbs_aggregate": world * bytes_pair * len(seq) / dt_copy / 1e9, "numa": numa}
+        # (1) ScenePipeline: pinned rasters, upload of pair i+1 overlapped with the matching of pair i
+        pipe.run(seq[: max(1, min(args.warmup, 2))])
+        dt, m2 = wall(lambda: pipe.run(seq))
+        (m2,) = _sum_over_ranks(dist, dev, world, float(m2))
+        e2e = {"value": m2 / dt, "unit": "matches/s", "h2d_bytes_per_step": bytes_pair,
+               "d2h_bytes_per_step": int(st.n_kept) * (5 * 4 + 8),
+               "scene_pairs_per_sec": world * len(seq) / dt, "ms_per_step": 1e3 * dt / len(seq),
+               "api": "karios_b200.api.ScenePipeline.run (pinned host rasters -> rows in pinned host memory)",
+               "frac_of_copy_ceiling": round(dt_copy / dt, 4)}
+        pipe.close()
+        del pipe
+
+        # (2) the reference's plugin API, as KariosAPI._compute_matches/_handle_klt_results call it
+        #     (api/core.py:845-891): NumPy rasters -> KLT.match -> DataFrame -> compute_zncc of the
+        #     score >= 0.4 rows.  Fresh raster objects every step, so every step uploads its pair.
+        import pandas as pd
+        from karios_b200.core import image as kimg
+        from karios_b200.matcher.klt import KLT
+        from karios_b200.matcher.zncc_service import ZNCCService
+
+        def as_np(t):
+            return t.view(torch.int16).numpy().view(np.uint16)
+
+        zs = ZNCCService()
+
+        def dropin_step(mon_np, ref_np):
+            mon_img, ref_img = kimg.ArrayRaster(mon_np), kimg.ArrayRaster(ref_np)
+            all_frame = pd.DataFrame()
+            for dataframe in KLT(conf).match(mon_img, ref_img, None):
+                cand = dataframe[dataframe["score"] >= 0.4]
+                dataframe["zncc_score"] = np.nan
+                z = zs.compute_zncc(cand, mon_img, ref_img)
+                dataframe.loc[cand.index, "zncc_score"] = z
+                all_frame = pd.concat([all_frame, dataframe])
+            return len(all_frame)
+
+        def dropin_run(pairs_np):
+            return sum(dropin_step(m, r) for m, r in pairs_np)
+
+        pinned_np = [(as_np(m), as_np(r)) for m, r in host_pairs]
+        seq_np = [pinned_np[i % len(pinned_np)] for i in range(n_e2e)]
+        dropin_run(seq_np[:2])
+        up0 = dict(kimg.uploads)
+        dt_d, m3 = wall(lambda: dropin_run(seq_np))
+        (m3,) = _sum_over_ranks(dist, dev, world, float(m3))
+        uploads_per_step = (kimg.uploads["count"] - up0["count"]) / len(seq_np)
+        e2e_dropin = {"value": m3 / dt_d, "unit": "matches/s", "scene_pairs_per_sec": world * len(seq_np) / dt_d,
+                      "ms_per_step": 1e3 * dt_d / len(seq_np), "h2d_bytes_per_step": bytes_pair,
+                      "d2h_bytes_per_step": int(st.n_kept) * (5 * 4 + 8),
+                      "raster_uploads_per_step": uploads_per_step,
+                      "api": "karios_b200.matcher.klt.KLT.match + ZNCCService.compute_zncc on NumPy rasters "
+                             "(pinned-memory backed), pandas DataFrames out: the calls of karios/api/core.py:845-891",
+                      "vs_scene_pipeline": round(dt_d / dt, 3)}
+        if rank == 0 and world == 1:
+            # the same through ordinary pageable NumPy arrays (what GDAL hands out today)
+            pag = [(np.array(m, copy=True), np.array(r, copy=True)) for m, r in pinned_np[:1]]
+            dropin_run(pag)
+            n_p = min(5, n_e2e)
+            dt_p, _ = wall(lambda: dropin_run(pag * n_p))
+            e2e_dropin["pageable_ms_per_step"] = round(1e3 * dt_p / n_p, 3)
+        del host_pairs, pinned_np, seq_np
+
+    # ---- CPU baseline beside it (rank 0, N = 1 only): the unmodified reference ------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        from oracle import oracle as O
         mon_h, ref_h = (t.cpu().view(torch.int16).numpy().view(np.uint16) for t in scenes[0])
-        cconf = default_conf(O.KLTConfiguration)
-        m, s, how = cpu_run(ref_h, mon_h, cconf)
-        cpu = {"value": m / s, "unit": "matches/s", "cores": os.cpu_count(), "kind": "port",
-               "sample": f"1 full {size}x{size} scene pair, default config, one run, {how}",
+        m, s, how = reference_pass(ref_h, mon_h)
+        cpu = {"value": m / s, "unit": "matches/s", "cores": os.cpu_count(), "kind": "reference",
+               "sample": f"1 full {size}x{size} scene pair (scene 0 of the CUDA arm), default config, one pass, "
+                         f"{how}; cv2.setNumThreads({os.cpu_count()})",
                "seconds": round(s, 3), "matches": m}
+        from oracle import oracle as O
         if "rows" in next_rows.get("mutual_info", {}):
             k = min(1500, int(st.n_kept))
             c4 = [c[:k].cpu().numpy() for c in cols]
@@ -472,13 +597,13 @@ def cuda_arm(args):
             next_rows["mutual_info"]["cpu_rows_per_sec"] = round(k / dt_mi, 1)
             next_rows["mutual_info"]["cpu_sample"] = f"{k} rows, oracle.mutual_info (np.histogram2d per row, 1 core)"
         if "ms" in next_rows.get("large_offset", {}):
-            side = min(size, 2048)
+            side_ = min(size, 2048)
             t0 = time.perf_counter()
-            O.phase_cross_correlation_shift(mon_h[:side, :side], ref_h[:side, :side])
+            O.phase_cross_correlation_shift(mon_h[:side_, :side_], ref_h[:side_, :side_])
             dt_lo = time.perf_counter() - t0
             next_rows["large_offset"]["cpu_seconds_sample"] = round(dt_lo, 3)
-            next_rows["large_offset"]["cpu_sample"] = (f"{side}x{side} crop, oracle (numpy.fft float64, 1 core); "
-                                                       f"the full frame is {(size / side) ** 2:.0f}x the pixels")
+            next_rows["large_offset"]["cpu_sample"] = (f"{side_}x{side_} crop, oracle (numpy.fft float64, 1 core); "
+                                                       f"the full frame is {(size / side_) ** 2:.0f}x the pixels")
             t0 = time.perf_counter()
             O.percentiles_2_98(mon_h)
             next_rows["percentiles_2_98"]["cpu_seconds"] = round(time.perf_counter() - t0, 3)
@@ -489,14 +614,13 @@ def cuda_arm(args):
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / max(1, args.steps),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
             "data": "synthetic",
-            "config": {"workload": WORKLOAD if size == S2 else f"synthetic_{size}x{size}_pair_klt_zncc",
-                       "scene": f"{size}x{size} uint16 pair, shift (+0.30,-0.20) px",
-                       "klt": "maxCorners 20000, minDistance 10, blocksize 15, winsize 25, q 0.1, k7, 1 tile",
-                       "parallelism": f"scene pairs sharded over {world} GPU(s), no data-path collective",
-                       "l2": "inputs (482 MB per pair) exceed the 126 MB L2; no flush needed",
-                       "scenes_per_rank": len(scenes), "pairs_in_flight": args.depth},
+            "config": bench_config(size, world),
+            "run": {"scenes_per_rank": len(scenes), "pairs_in_flight": args.depth,
+                    "timed_batches": [round(b["ms"], 4) for b in batches], "reported": "median batch",
+                    "numa": numa},
             "scene_pairs_per_sec": pairs_per_sec,
             "matches_per_scene": matches / max(1, world * args.steps),
+            "single_pair_latency_ms": round(single_pair_ms, 4),
             "roofline": roofline,
             "path_hbm": {"alg_bytes_per_pair": total_alg, "kernel_ms_per_pair": round(total_ms, 4),
                          "gbs": round(total_alg / (total_ms * 1e6), 1) if total_ms > 0 else None,
@@ -504,8 +628,13 @@ def cuda_arm(args):
             "stages": stages,
             "cpu_baseline": cpu,
             "e2e": e2e,
+            "e2e_dropin": e2e_dropin,
+            "h2d_ceiling": h2d,
             "next_rows": next_rows,
-            "pipeline": pipeline_diag, "exchange_ms": round(exchange_ms, 3), "gpu_launches": 27 * args.steps * len(sm.windows),      # own kernels per tile (profiles/ncu_launches_r1_v11.csv)
+            "pipeline": {"redo_units": max(b["redo_units"] for b in batches),
+                         "max_unit_gap_ms": max((b["max_unit_gap_ms"] or 0) for b in batches)},
+            "exchange_ms": round(exchange_ms, 3), "exchange_moments": diag,
+            "gpu_launches": launches,      # kr_launch_count() over one timed batch (this rank)
             "clocks": sampler.summary(),
             "stats_last": {k: v for k, v in st.as_dict().items() if k.startswith("n_") or k == "nms_rounds"},
         }

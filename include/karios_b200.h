@@ -106,6 +106,10 @@ typedef struct {
 
 KR_API int kr_version(void);
 KR_API const char *kr_last_error(void);
+/* Kernel launches issued by this library since it was loaded (process-wide,
+ * monotonic).  Measurement aid: bench.py reports the difference over its timed
+ * region as "gpu_launches".  Replaces nothing in the reference. */
+KR_API uint64_t kr_launch_count(void);
 
 /* Workspace sized for tiles up to max_w x max_h and max_corners corners
  * (<= 0: up to one corner per candidate).  Replaces nothing: cv2/NumPy allocate
@@ -278,6 +282,21 @@ KR_API int kr_count_valid(const void *img, int64_t pitch, int dtype, int w, int 
  * _filter_by_dn_values (karios/api/core.py:687-728), DEM altitudes (:1050-1053). */
 KR_API int kr_gather_points(const void *img, int64_t pitch, int dtype, int w, int h, const float *x0,
                             const float *y0, int n, double *out, void *stream);
+
+/* Multi-GPU exchange record of one unit (a tile of a scene pair): written on the
+ * device, stream-ordered after kr_match_tile, so that the match tables of a batch
+ * can be collected with ONE fixed-size all_gather and no host synchronisation
+ * (the statistics karios/accuracy_analysis/accuracy_statistics.py
+ * derives from dx / dy start from these moments).  128 bytes. */
+typedef struct {
+    int32_t n_rows;                 /* rows of the unit (kr_stats.n_kept) */
+    int32_t flags;                  /* bit 0: select_incomplete, bit 1: overflow */
+    double n;                       /* n_rows as float64 */
+    double sum_dx, sum_dy, sum_dx2, sum_dy2;
+    double min_dx, min_dy, max_dx, max_dy;      /* +inf / -inf when n_rows == 0 */
+    double reserved[6];
+} kr_unit_header;
+KR_API int kr_unit_header_write(kr_ctx *ctx, kr_rows rows, kr_unit_header *d_out, void *stream);
 
 /* Measurement hooks (no reference counterpart).  With profiling on, kr_match_tile
  * brackets its stages with CUDA events on the caller's stream; after the stream

@@ -20,12 +20,12 @@ KR_U8, KR_U16, KR_I16, KR_F32 = 0, 1, 2, 3
 KR_TAIL_NONE, KR_TAIL_AVX512 = 0, 32
 
 EXPORTS = [
-    "kr_version", "kr_last_error", "kr_ctx_create", "kr_ctx_destroy", "kr_read_stats",
+    "kr_version", "kr_last_error", "kr_launch_count", "kr_ctx_create", "kr_ctx_destroy", "kr_read_stats",
     "kr_set_select_all", "kr_set_corner_mode", "kr_minmax_mask", "kr_u8_laplacian", "kr_corner_min_eigen_val",
     "kr_good_features", "kr_pyr_down", "kr_pyr_lk", "kr_klt_track", "kr_zncc", "kr_mutual_info",
     "kr_match_tile", "kr_auto_ksize", "kr_auto_ksize_scratch_bytes",
     "kr_set_profiling", "kr_read_stage_ms",
-    "kr_cross_power", "kr_argmax_abs", "kr_shift_image", "kr_histogram", "kr_count_valid",
+    "kr_unit_header_write", "kr_cross_power", "kr_argmax_abs", "kr_shift_image", "kr_histogram", "kr_count_valid",
     "kr_gather_points",
 ]
 NUM_STAGES = 12
@@ -73,6 +73,14 @@ class Rows(C.Structure):
                 ("mi", C.c_void_p), ("capacity", C.c_int32)]
 
 
+class UnitHeader(C.Structure):
+    """kr_unit_header: exchange record header of one unit (128 bytes)."""
+    _fields_ = [("n_rows", C.c_int32), ("flags", C.c_int32), ("n", C.c_double), ("sum_dx", C.c_double),
+                ("sum_dy", C.c_double), ("sum_dx2", C.c_double), ("sum_dy2", C.c_double),
+                ("min_dx", C.c_double), ("min_dy", C.c_double), ("max_dx", C.c_double),
+                ("max_dy", C.c_double), ("reserved", C.c_double * 6)]
+
+
 _lib = None
 _lib_lock = threading.Lock()
 
@@ -95,6 +103,7 @@ def load_library(path: str = LIB_PATH):
         vp, i32, i64, f64 = C.c_void_p, C.c_int, C.c_int64, C.c_double
         L.kr_version.restype = i32
         L.kr_last_error.restype = C.c_char_p
+        L.kr_launch_count.restype = C.c_uint64
         L.kr_ctx_create.argtypes = [i32, i32, i32, i32, C.POINTER(vp)]
         L.kr_ctx_destroy.argtypes = [vp]
         L.kr_ctx_destroy.restype = None
@@ -122,6 +131,7 @@ def load_library(path: str = LIB_PATH):
         L.kr_auto_ksize_scratch_bytes.argtypes = [i32, i32, i32, i32, i32, i32]
         L.kr_auto_ksize.argtypes = [vp, vp, i64, vp, i64, i32, i32, i32, vp, i64, i32, f64, i32, f64,
                                     C.POINTER(KltConf), C.POINTER(C.c_int32), i32, vp, i64, Rows, vp, vp]
+        L.kr_unit_header_write.argtypes = [vp, Rows, vp, vp]
         L.kr_cross_power.argtypes = [vp, vp, i64, i32, vp]
         L.kr_argmax_abs.argtypes = [vp, i64, i32, vp, vp, vp]
         L.kr_shift_image.argtypes = [vp, i64, vp, i64, i32, i32, i32, i32, i32, vp]
@@ -129,7 +139,8 @@ def load_library(path: str = LIB_PATH):
         L.kr_count_valid.argtypes = [vp, i64, i32, i32, i32, vp, i64, vp, vp]
         L.kr_gather_points.argtypes = [vp, i64, i32, i32, i32, vp, vp, i32, vp, vp]
         for name in EXPORTS:
-            if name not in ("kr_last_error", "kr_ctx_destroy", "kr_version", "kr_auto_ksize_scratch_bytes"):
+            if name not in ("kr_last_error", "kr_ctx_destroy", "kr_version", "kr_launch_count",
+                            "kr_auto_ksize_scratch_bytes"):
                 getattr(L, name).restype = i32
         L.kr_auto_ksize_scratch_bytes.restype = i64
         _lib = L
@@ -222,9 +233,17 @@ class RowBuffers:
         # [0] = mutual_info_score (Studholme), [1] = mi_score (api/core.py:894-907)
         self.mi = torch.empty((2, self.capacity), dtype=torch.float64, device=device) if with_mi else None
 
+    @classmethod
+    def from_views(cls, capacity: int, f32: torch.Tensor, zncc=None, mi=None):
+        """Row buffers over existing device memory: f32 [5, >= capacity] (unit column
+        stride, any row stride), zncc [>= capacity] float64, mi [2, >= capacity] float64."""
+        self = cls.__new__(cls)
+        self.capacity, self.f32, self.zncc, self.mi = int(capacity), f32, zncc, mi
+        return self
+
     def struct(self) -> Rows:
         r = Rows()
-        base, step = self.f32.data_ptr(), self.capacity * 4
+        base, step = self.f32.data_ptr(), self.f32.stride(0) * 4
         r.x0, r.y0, r.dx, r.dy, r.score = (base + i * step for i in range(5))
         r.zncc = self.zncc.data_ptr() if self.zncc is not None else None
         r.mutual_info = self.mi[0].data_ptr() if self.mi is not None else None
@@ -445,6 +464,11 @@ class Context:
             int(x_off), int(y_off), int(tw), int(th), int(nodata_mon is not None),
             float(nodata_mon or 0), int(nodata_ref is not None), float(nodata_ref or 0),
             C.byref(kconf), rows.struct(), _stream()))
+
+    def unit_header(self, rows: RowBuffers, header: torch.Tensor):
+        """Enqueue kr_unit_header_write: count + dx / dy moments of the unit just matched into
+        `header` (32 float32 words of an exchange record, karios_b200/sharding.py)."""
+        _check(self.lib.kr_unit_header_write(self._h, rows.struct(), header.data_ptr(), _stream()))
 
     def match_tile(self, mon, ref, mask, window, kconf, rows, nodata_mon=None, nodata_ref=None):
         """match_tile_async + stats; re-runs once with every candidate when the

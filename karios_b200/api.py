@@ -43,6 +43,11 @@ class SceneMatcher:
         if isinstance(conf.laplacian_kernel_size, str) or conf.laplacian_invert_polarity == "auto":
             raise N.KariosB200Error("SceneMatcher handles fixed kernel size / polarity; "
                                     "use matcher.klt.KLT for the 'auto' searches")
+        if conf.outliers_filtering:
+            # klt.py:161-163 filters the rows of a tile on the host, in OpenCV order, before the
+            # frame is built and before ZNCC; the fused device sequence here has no such step
+            raise N.KariosB200Error("SceneMatcher does not apply outliers_filtering; "
+                                    "use matcher.klt.KLT (it filters per tile like the reference)")
         self.conf = conf
         self.h, self.w = h, w
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
@@ -59,17 +64,28 @@ class SceneMatcher:
         # latency-bound stages of one (selection, NMS, sorts) overlap the
         # bandwidth / issue-bound stages of the others
         self.depth = max(1, int(depth))
+        # hook of the multi-GPU exchange: called with (arena, unit streams) right after the last
+        # unit of a match_many call has been enqueued (sharding.exchange on a side stream)
+        self.on_last_enqueued = None
         self._slots = [(self.ctx, self.rows, torch.cuda.Stream(device=self.device))]
         for _ in range(self.depth - 1):
             self._slots.append((N.Context(tw, th, int(conf.maxCorners), self.device),
                                 N.RowBuffers(cap, self.device, with_zncc=True, with_mi=self.with_mi),
                                 torch.cuda.Stream(device=self.device)))
 
+    def _check_device(self):
+        """Kernels are enqueued on the current stream of the current device: it has to be the
+        device the workspace lives on."""
+        if torch.cuda.current_device() != (self.device.index or 0):
+            raise N.KariosB200Error(f"current CUDA device {torch.cuda.current_device()} is not the matcher's "
+                                    f"{self.device}; wrap the call in torch.cuda.device(...)")
+
     def match_device(self, mon: torch.Tensor, ref: torch.Tensor, mask=None, nodata=(None, None),
                      collect=True):
         """Both rasters resident in HBM.  -> (list of per-tile [6, n] float64-free
         device tensors (x0,y0,dx,dy,score) + zncc, total rows)."""
         tiles, total = [], 0
+        self._check_device()
         for win in self.windows:
             st = self.ctx.match_tile(mon, ref, mask, win, self.kconf, self.rows, nodata[0], nodata[1])
             n = int(st.n_kept)
@@ -85,28 +101,34 @@ class SceneMatcher:
 
     def match_many(self, pairs, mask=None, nodata=(None, None), collect=True):
         """pairs: iterable of (mon, ref) CUDA tensors.  Every tile of every pair is
-        one unit of work; unit k runs on slot k mod depth (own context, row buffers
-        and stream) and is finalised -- counts read, rows cloned -- only when its
-        slot is needed again, so up to `depth` units overlap on the device.
-        -> (list per pair of per-tile (rows, zncc[, mi]) tuples, total rows)."""
+        one unit of work; unit k runs on slot k mod depth (own context and stream) and
+        is finalised -- counts read -- only when its slot is needed again, so up to
+        `depth` units overlap on the device.  The kernels write the rows of unit k and
+        its exchange header straight into record k of one arena (karios_b200/sharding.py:
+        the arena is the payload of the multi-GPU exchange; no copy, no packing).
+        -> (list per pair of per-tile (rows, zncc[, mi]) views into the arena, total rows)."""
+        from karios_b200 import sharding
         results, total = [], 0
         pairs = list(pairs)
+        self._check_device()
         # One result arena for the whole call, allocated before any unit is in flight: nothing
         # inside the pipelined loop touches the allocator (a cudaMalloc of the caching allocator
         # while four units are in flight was measured to stall the host for 10-40 ms).
         n_units = len(pairs) * len(self.windows)
         cap = self.rows.capacity
-        arena_f32 = torch.empty((max(n_units, 1), 5, cap), dtype=torch.float32, device=self.device)
-        arena_z = torch.empty((max(n_units, 1), cap), dtype=torch.float64, device=self.device)
+        arena = sharding.new_arena(n_units, cap, self.device)
         arena_mi = torch.empty((max(n_units, 1), 2, cap), dtype=torch.float64, device=self.device) \
             if self.with_mi else None
         self.n_redo, self.redo_flags, self.unit_done_t = 0, [], []     # diagnostics of the last call
         self.unit_events = []
         self.trace_units = getattr(self, "trace_units", False)
-        # the arena and the rows per unit of the last call (sharding.gather_units packs from here)
-        self.last_arena, self.last_counts = (arena_f32, arena_z, arena_mi), [0] * n_units
+        self.last_arena, self.last_counts = arena, [0] * n_units
         inflight = [None] * self.depth
         cur = torch.cuda.current_stream(self.device)
+
+        def unit_rows(unit):
+            hdr, f32, z = sharding.unit_views(arena, unit, cap)
+            return hdr, N.RowBuffers.from_views(cap, f32, z, arena_mi[unit] if self.with_mi else None)
 
         def finalise(slot):
             nonlocal total
@@ -114,8 +136,8 @@ class SceneMatcher:
             if job is None:
                 return
             inflight[slot] = None
-            ctx, rows, stream = self._slots[slot]
-            pair_idx, mon, ref, win, unit = job
+            ctx, _, stream = self._slots[slot]
+            pair_idx, mon, ref, win, unit, hdr, rows = job
             with torch.cuda.stream(stream):
                 st = ctx.read_stats()
                 self.unit_done_t.append(time.perf_counter())
@@ -124,18 +146,18 @@ class SceneMatcher:
                     self.redo_flags.append((int(st.two_tier_fallback), int(st.overflow), int(st.n_corners),
                                             int(st.n_sorted), int(st.nms_rounds)))
                     st = ctx.match_tile(mon, ref, mask, win, self.kconf, rows, nodata[0], nodata[1])
+                    ctx.unit_header(rows, hdr)
                 n = int(st.n_kept)
                 if (mask is None and st.valid == 0) or st.n_corners == 0:
+                    if n:                          # tile skipped by the reference: no rows
+                        hdr.zero_()
                     return
                 total += n
-                self.last_counts[unit] = n if collect else 0
+                self.last_counts[unit] = n
                 if collect:
-                    t = (arena_f32[unit, :, :n], arena_z[unit, :n])
-                    t[0].copy_(rows.f32[:, :n])
-                    t[1].copy_(rows.zncc[:n])
+                    t = (rows.f32[:, :n], rows.zncc[:n])
                     if self.with_mi:
-                        t = t + (arena_mi[unit, :, :n],)
-                        t[2].copy_(rows.mi[:, :n])
+                        t = t + (rows.mi[:, :n],)
                     results[pair_idx].append(t)
 
         k = 0
@@ -144,7 +166,8 @@ class SceneMatcher:
             for win in self.windows:
                 slot = k % self.depth
                 finalise(slot)
-                ctx, rows, stream = self._slots[slot]
+                ctx, _, stream = self._slots[slot]
+                hdr, rows = unit_rows(k)
                 stream.wait_stream(cur)
                 with torch.cuda.stream(stream):
                     if self.trace_units:
@@ -152,11 +175,14 @@ class SceneMatcher:
                         ev[0].record()
                         t_enq = time.perf_counter()
                     ctx.match_tile_async(mon, ref, mask, win, self.kconf, rows, nodata[0], nodata[1])
+                    ctx.unit_header(rows, hdr)
                     if self.trace_units:
                         ev[1].record()
                         self.unit_events.append(ev + (t_enq, time.perf_counter()))
-                inflight[slot] = (pair_idx, mon, ref, win, k)
+                inflight[slot] = (pair_idx, mon, ref, win, k, hdr, rows)
                 k += 1
+                if k == n_units and self.on_last_enqueued is not None:
+                    self.on_last_enqueued(arena, [s for _, _, s in self._slots])
         for j in range(self.depth):
             finalise((k + j) % self.depth)
         for _, _, stream in self._slots:
@@ -223,12 +249,30 @@ class ScenePipeline:
             self.ready[slot].record(self.copy_stream)
         del cur
 
+    def copy_only(self, pairs):
+        """The uploads of run() without any kernel: the host-to-device ceiling of this
+        pipeline on this box (bench.py reports run() as a fraction of it)."""
+        if not pairs:
+            return
+        cur = torch.cuda.current_stream()
+        for s in range(2):
+            self.free[s].record(cur)
+        self._upload(0, *pairs[0])
+        for i in range(len(pairs)):
+            slot = i & 1
+            if i + 1 < len(pairs):
+                self._upload(slot ^ 1, *pairs[i + 1])
+            cur.wait_event(self.ready[slot])
+            self.free[slot].record(cur)
+        cur.synchronize()
+
     def run(self, pairs):
         """pairs: list of (mon_host, ref_host) pinned tensors.  Returns the total
         number of matches; the rows of the last pair stay in host_rows/host_zncc."""
         total = 0
         if not pairs:
             return 0
+        self.sm._check_device()
         for s in range(2):
             self.free[s].record(torch.cuda.current_stream())
         self._upload(0, *pairs[0])

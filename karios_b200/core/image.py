@@ -3,8 +3,74 @@ matcher only needs .read/.array/.x_size/.y_size/.no_data_value/.clear_cache.
 DeviceRaster keeps the raster in HBM so tiles are windows, not copies."""
 from __future__ import annotations
 
+import threading
+import weakref
+
 import numpy as np
 import torch
+
+# ---------------------------------------------------------------------------
+# Device copies of host rasters.  The reference reads a raster from disk once per
+# consumer (KLT.match tile reads, then .array for ZNCC and for each of the two
+# mutual-information services, karios/api/core.py:845-907, each followed by
+# clear_cache()).  Here the whole raster is uploaded ONCE per raster object and the
+# copy is shared by every consumer (tiles are windows of it).  Rasters are
+# file-backed and immutable in KARIOS; the copy is keyed by the object (weakly:
+# it is freed with the object) and at most _CACHE_MAX rasters are kept.
+_CACHE: "weakref.WeakKeyDictionary" = weakref.WeakKeyDictionary()
+_CACHE_ORDER: list = []            # weak references, oldest first
+_CACHE_MAX = 8
+_CACHE_LOCK = threading.Lock()
+uploads = {"count": 0, "bytes": 0}        # host -> device raster copies made so far (diagnostic)
+
+
+def device_full(img, dev, as_mask: bool = False) -> torch.Tensor:
+    """The whole raster of `img` as a 2-D tensor on `dev` (uint8 0/1 for a mask)."""
+    from karios_b200 import _native as N
+    full = getattr(img, "device_array", None)
+    if full is not None:
+        if as_mask and full.dtype != torch.uint8:
+            full = (full > 0).to(torch.uint8)
+        return full
+    key = (dev.index, bool(as_mask))
+    try:
+        with _CACHE_LOCK:
+            ent = _CACHE.get(img)
+            if ent is not None and key in ent:
+                return ent[key]
+    except TypeError:                      # unhashable / not weak-referenceable raster object
+        ent = None
+    t = N.to_device(img.array, dev)
+    uploads["count"] += 1
+    uploads["bytes"] += t.numel() * t.element_size()
+    if as_mask and t.dtype != torch.uint8:
+        t = (t > 0).to(torch.uint8)
+    try:
+        with _CACHE_LOCK:
+            _CACHE.setdefault(img, {})[key] = t
+            _CACHE_ORDER[:] = [r for r in _CACHE_ORDER if r() is not None and r() is not img]
+            _CACHE_ORDER.append(weakref.ref(img))
+            while len(_CACHE_ORDER) > _CACHE_MAX:
+                old = _CACHE_ORDER.pop(0)()
+                if old is not None:
+                    _CACHE.pop(old, None)
+    except TypeError:
+        pass
+    return t
+
+
+def release_device(img=None) -> None:
+    """Drop the device copy of `img` (all rasters when None), e.g. after the host
+    array of an in-memory raster was modified in place."""
+    with _CACHE_LOCK:
+        if img is None:
+            _CACHE.clear()
+            _CACHE_ORDER.clear()
+        else:
+            try:
+                _CACHE.pop(img, None)
+            except TypeError:
+                pass
 
 
 class ArrayRaster:

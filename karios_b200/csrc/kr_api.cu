@@ -4,8 +4,12 @@
 #include <string.h>
 #include <stdlib.h>
 #include <math.h>
+#include <atomic>
 #include <new>
 #include "kr_internal.cuh"
+
+static std::atomic<unsigned long long> g_launches{0};
+void kr_note_launch(void) { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
 static thread_local char g_err[512] = "";
 
@@ -89,6 +93,42 @@ __global__ void k_auto_copy(const kr_auto_result *r, AutoKs ks, const float *all
     }
 }
 
+
+static_assert(sizeof(kr_unit_header) == 128, "kr_unit_header is 128 bytes (karios_b200/sharding.py)");
+// count + dx / dy moments of the rows of the unit just matched (one block)
+__global__ void __launch_bounds__(256) k_unit_header(const KrDevStats *st, kr_rows rows, kr_unit_header *out)
+{
+    __shared__ double sh[8][8];
+    uint32_t n = st->n_kept;
+    if (n > (uint32_t)rows.capacity) n = rows.capacity;
+    double sx = 0, sy = 0, sxx = 0, syy = 0, mnx = INFINITY, mny = INFINITY, mxx = -INFINITY, mxy = -INFINITY;
+    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
+        const double dx = rows.dx[i], dy = rows.dy[i];
+        sx += dx; sy += dy; sxx += dx * dx; syy += dy * dy;
+        mnx = fmin(mnx, dx); mny = fmin(mny, dy); mxx = fmax(mxx, dx); mxy = fmax(mxy, dy);
+    }
+    double v[8] = {sx, sy, sxx, syy, mnx, mny, mxx, mxy};
+    for (int o = 16; o; o >>= 1)
+        for (int k = 0; k < 8; k++) {
+            const double t = __shfl_xor_sync(0xffffffffu, v[k], o);
+            v[k] = k < 4 ? v[k] + t : (k < 6 ? fmin(v[k], t) : fmax(v[k], t));
+        }
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0)
+        for (int k = 0; k < 8; k++) sh[warp][k] = v[k];
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < 8; w++)
+            for (int k = 0; k < 8; k++)
+                sh[0][k] = k < 4 ? sh[0][k] + sh[w][k] : (k < 6 ? fmin(sh[0][k], sh[w][k]) : fmax(sh[0][k], sh[w][k]));
+        out->n_rows = (int32_t)n;
+        out->flags = (st->select_incomplete ? 1 : 0) | (st->overflow ? 2 : 0);
+        out->n = (double)n;
+        out->sum_dx = sh[0][0]; out->sum_dy = sh[0][1]; out->sum_dx2 = sh[0][2]; out->sum_dy2 = sh[0][3];
+        out->min_dx = sh[0][4]; out->min_dy = sh[0][5]; out->max_dx = sh[0][6]; out->max_dy = sh[0][7];
+        for (int k = 0; k < 6; k++) out->reserved[k] = 0.0;
+    }
+}
 
 template <typename T> int dev_alloc(T **p, size_t count)
 {
@@ -183,6 +223,7 @@ extern "C" {
 
 KR_API int kr_version(void) { return 100; }
 KR_API const char *kr_last_error(void) { return g_err; }
+KR_API uint64_t kr_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
 KR_API int kr_ctx_create(int device, int max_w, int max_h, int max_corners, kr_ctx **out)
 {
@@ -277,6 +318,15 @@ KR_API void kr_ctx_destroy(kr_ctx *c)
     cudaFree(c->d_p0); cudaFree(c->d_p1); cudaFree(c->d_d); cudaFree(c->d_keep);
     if (c->ev[0]) for (int i = 0; i <= KR_NUM_STAGES; i++) cudaEventDestroy(c->ev[i]);
     delete c;
+}
+
+KR_API int kr_unit_header_write(kr_ctx *ctx, kr_rows rows, kr_unit_header *d_out, void *stream)
+{
+    if (!ctx || !d_out) return kr_set_error(KR_ERR_INVALID, "NULL argument");
+    if (!rows.dx || !rows.dy || rows.capacity < 1) return kr_set_error(KR_ERR_INVALID, "incomplete rows");
+    k_unit_header<<<1, 256, 0, (cudaStream_t)stream>>>(ctx->d_stats, rows, d_out);
+    KR_LAUNCH_CHECK();
+    return KR_OK;
 }
 
 KR_API int kr_set_select_all(kr_ctx *ctx, int on)

@@ -1021,6 +1021,7 @@ int krl_good_features(kr_ctx *ctx, const uint8_t *img, int64_t pitch, const uint
                             &md2, &st, &key_cap, &mc, &max_rounds};
             KR_CUDA(cudaLaunchCooperativeKernel((const void *)k_nms, dim3(ctx->nms_grid), dim3(256), args,
                                                 0, s));
+            kr_note_launch();
         } else {
             const int ng = ctx->num_sms * 2;
             k_nms_init<<<ng, 256, 0, s>>>(keys, xy, state, next, head, w, cell, gw, st, key_cap);

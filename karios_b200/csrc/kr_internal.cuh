@@ -82,7 +82,14 @@ int kr_set_error(int code, const char *fmt, ...);
             return kr_set_error(KR_ERR_CUDA, "%s: %s (%s:%d)", #expr,                  \
                                 cudaGetErrorString(_e), __FILE__, __LINE__);           \
     } while (0)
-#define KR_LAUNCH_CHECK() KR_CUDA(cudaGetLastError())
+// every kernel launch of the library is followed by KR_LAUNCH_CHECK(): it also counts the launch
+// (kr_launch_count, process-wide; bench.py reports the difference over its timed region)
+void kr_note_launch(void);
+#define KR_LAUNCH_CHECK()            \
+    do {                             \
+        kr_note_launch();            \
+        KR_CUDA(cudaGetLastError()); \
+    } while (0)
 #define KR_TRY(expr)                 \
     do {                             \
         int _r = (expr);             \

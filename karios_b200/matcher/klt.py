@@ -24,6 +24,7 @@ import torch
 from pandas import DataFrame
 
 from karios_b200 import _native as N
+from karios_b200.core.image import device_full
 
 logger = logging.getLogger(__name__)
 
@@ -50,25 +51,29 @@ def get_context(w: int, h: int, max_corners: int) -> N.Context:
     return ctx
 
 
-def _filter_outliers(x0, y0, x1, y1, score):
-    """klt.py:52-71 (O(N) on <= maxCorners rows: stays in NumPy)."""
-    dx = x1 - x0
-    dy = y1 - y0
+def _outlier_keep(dx, dy):
+    """Rows kept by klt.py:52-71 (iterated 3-sigma / 20 px test on dx, dy), as a boolean
+    mask over the input rows.  O(N) on <= maxCorners rows: stays in NumPy, float32 like the
+    reference; the rows must be in the reference's (OpenCV) order so that the float32
+    means and deviations are summed in the same order."""
+    keep = np.arange(len(dx))
     while True:
         ind = ((np.abs(dx - dx.mean()) < 3 * dx.std()) & (np.abs(dy - dy.mean()) < 3 * dy.std())
                & (np.abs(dx - dx.mean()) < 20) & (np.abs(dy - dy.mean()) < 20))
         if ind.sum() == len(dx):
             break
-        dx, dy, x0, x1, y0, y1, score = dx[ind], dy[ind], x0[ind], x1[ind], y0[ind], y1[ind], score[ind]
-    return x0, y0, x1, y1, score
+        dx, dy, keep = dx[ind], dy[ind], keep[ind]
+    return keep
 
 
 def _frame(cols: np.ndarray, conf) -> DataFrame:
-    """[5, n] float32 (x0, y0, dx, dy, score) -> the DataFrame of klt.py:166-168."""
+    """[5, n] float32 (x0, y0, dx, dy, score) -> the DataFrame of klt.py:166-168.  dx / dy are
+    the kernel's float32 differences p1 - p0 of tile-local coordinates, i.e. the reference's
+    `x1 - x0`; they are never rebuilt from offset coordinates."""
     x0, y0, dx, dy, score = (cols[i] for i in range(5))
     if conf.outliers_filtering and len(x0):
-        x0, y0, x1, y1, score = _filter_outliers(x0, y0, x0 + dx, y0 + dy, score)
-        dx, dy = x1 - x0, y1 - y0
+        keep = _outlier_keep(dx, dy)
+        x0, y0, dx, dy, score = x0[keep], y0[keep], dx[keep], dy[keep], score[keep]
     return DataFrame.from_dict({"x0": x0, "y0": y0, "dx": dx, "dy": dy, "score": score})
 
 
@@ -140,10 +145,12 @@ class KLT:
 
     @staticmethod
     def _box(img, dev, x_off, y_off, x_size, y_size):
-        """(tensor holding the tile, window inside it)."""
-        full = getattr(img, "device_array", None)
-        if full is not None:
-            return full, (x_off, y_off, x_size, y_size)
+        """(tensor holding the tile, window inside it).  A host raster is uploaded once
+        as a whole (core.image.device_full: shared with the scoring services, which need
+        the whole raster anyway, zncc_service.py:209-210) and tiles are windows of it; a
+        raster without `.array` is read tile by tile like the reference does (klt.py:251)."""
+        if getattr(img, "device_array", None) is not None or hasattr(img, "array"):
+            return device_full(img, dev), (x_off, y_off, x_size, y_size)
         box = N.to_device(img.read(1, x_off, y_off, x_size, y_size), dev)
         return box, (0, 0, x_size, y_size)
 
@@ -166,18 +173,21 @@ class KLT:
         if mask:
             logger.info("Read mask at offset x %s, y %s, with tile size %s, %s", x_off, y_off,
                         x_size, y_size)
-            mfull = getattr(mask, "device_array", None)
-            if mfull is not None and win[0] == x_off and win[1] == y_off:
-                mask_t = mfull
+            whole = getattr(mask, "device_array", None) is not None or hasattr(mask, "array")
+            if whole and win[0] == x_off and win[1] == y_off:
+                mask_t = device_full(mask, dev, as_mask=True)      # uint8 0/1, same frame as the rasters
+                if mask_t.shape != mon_t.shape:
+                    raise N.KariosB200Error("mask and rasters differ in size")
             else:
-                mb = mask.read(1, x_off, y_off, x_size, y_size)
-                mask_t = N.to_device(mb, dev)
-                if mask_t.dtype != torch.uint8:
-                    mask_t = (mask_t > 0).to(torch.uint8)
-                if win[0] or win[1]:       # rasters on device, mask on host: pad to raster frame
+                mb = device_full(mask, dev, as_mask=True)[y_off:y_off + y_size, x_off:x_off + x_size] \
+                    if whole else N.to_device(mask.read(1, x_off, y_off, x_size, y_size), dev)
+                mask_t = mb if mb.dtype == torch.uint8 else (mb > 0).to(torch.uint8)
+                if win[0] or win[1]:       # rasters as whole frames, mask as a tile: pad to raster frame
                     full = torch.zeros(mon_t.shape, dtype=torch.uint8, device=dev)
                     full[y_off:y_off + y_size, x_off:x_off + x_size] = mask_t
                     mask_t = full
+                elif not mask_t.is_contiguous():
+                    mask_t = mask_t.contiguous()
         ctx = get_context(x_size, y_size, int(conf.maxCorners))
         cap = int(conf.maxCorners) if conf.maxCorners > 0 else ctx._cap_unlimited(x_size, y_size)
         rows = N.RowBuffers(cap, dev, with_zncc=False)
@@ -230,6 +240,8 @@ class KLT:
         if conf.laplacian_kernel_size == "auto":
             return self._auto_ksize(ctx, mon_t, ref_t, mask_t, win, rows, nd, invert)
         kconf = N.make_conf(conf, invert_mon=invert, tail_mode=self._tail_mode)
+        if conf.outliers_filtering:
+            return self._track_once_unsorted(ctx, mon_t, ref_t, mask_t, win, rows, nd, invert, kconf)
         st = ctx.match_tile(mon_t, ref_t, mask_t, win, kconf, rows, nd[0], nd[1])
         if mask_t is None and st.valid == 0:
             logger.info("-- No valid pixels, skipping this tile")
@@ -243,7 +255,28 @@ class KLT:
         df.attrs["kr_state"] = "final" if (win[0] or win[1]) else "sorted"
         return df, int(st.n_corners), (kconf.ksize_mon, kconf.ksize_ref)
 
-    def _planes(self, ctx, mon_t, ref_t, mask_t, win, nd, invert, ksizes):
+    def _track_once_unsorted(self, ctx, mon_t, ref_t, mask_t, win, rows, nd, invert, kconf):
+        """Fixed kernel size with outliers_filtering: the filter (klt.py:161-163) runs on the
+        rows in OpenCV order and tile-local coordinates, before offsets and the (x0, y0) sort,
+        so the stages are called one by one (kr_minmax_mask, kr_u8_laplacian, kr_klt_track)
+        instead of the fused kr_match_tile, which sorts on the device."""
+        conf = self._conf
+        mk, rk = int(kconf.ksize_mon), int(kconf.ksize_ref)
+        planes = self._planes(ctx, mon_t, ref_t, mask_t, win, nd, invert, None, pair=(mk, rk))
+        if planes is None:
+            if mask_t is None:
+                logger.info("-- No valid pixels, skipping this tile")
+            return None
+        m, mon_l, ref_l = planes
+        tconf = N.make_conf(conf, ksize_mon=1, ksize_ref=1, invert_mon=False, tail_mode=self._tail_mode)
+        n_init, n_kept = ctx.klt_track(ref_l[rk], mon_l[mk], m, tconf, rows, None)
+        if n_init == 0:
+            return None
+        df = _frame(rows.f32[:, :n_kept].cpu().numpy(), conf)
+        df.attrs["kr_state"] = "raw"
+        return df, int(n_init), (mk, rk)
+
+    def _planes(self, ctx, mon_t, ref_t, mask_t, win, nd, invert, ksizes, pair=None):
         """Auto mask (when needed), min/max and Laplacians for a set of sizes."""
         x, y, w, h = win
         mon_b = mon_t[y:y + h, x:x + w]
@@ -257,8 +290,8 @@ class KLT:
             valid = int(torch.count_nonzero(m).item())
         if valid == 0:
             return None
-        mon_l = {k: ctx.u8_laplacian(mon_b, k, invert=invert, slot=0) for k in ksizes}
-        ref_l = {k: ctx.u8_laplacian(ref_b, k, invert=False, slot=1) for k in ksizes}
+        mon_l = {k: ctx.u8_laplacian(mon_b, k, invert=invert, slot=0) for k in (ksizes or [pair[0]])}
+        ref_l = {k: ctx.u8_laplacian(ref_b, k, invert=False, slot=1) for k in (ksizes or [pair[1]])}
         return m, mon_l, ref_l
 
     def _auto_ksize_device(self, ctx, mon_t, ref_t, mask_t, win, rows, nd, invert):

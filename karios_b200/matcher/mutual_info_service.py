@@ -34,9 +34,12 @@ class MutualInfoService:
         if len(df) == 0:
             score = Series(np.empty(0, np.float64), index=df.index, dtype=np.float64)
         else:
-            ref, mon, cols = _score_inputs(df, monitored, reference)
-            mi = get_context(64, 64, 1024).mutual_info(ref, mon, *cols)
-            score = Series(mi[0].cpu().numpy(), index=df.index, dtype=np.float64)
+            inp = _score_inputs(df, monitored, reference)
+            if inp is None:
+                score = Series(np.full(len(df), np.nan), index=df.index, dtype=np.float64)
+            else:
+                mi = get_context(64, 64, 1024).mutual_info(*inp[:2], *inp[2])
+                score = Series(mi[0].cpu().numpy(), index=df.index, dtype=np.float64)
         monitored.clear_cache()
         reference.clear_cache()
         logger.info("Mutual information computation finish")

@@ -4,8 +4,11 @@
     where the reference yields NaN: chip outside the raster, zero variance)
 
 The per-row Python loop of the reference (`df.apply`, zncc_service.py:177) is
-one kernel launch here (kr_zncc); `_zncc2` itself is kept as a host helper with
-the reference's argument checks for API parity (zncc_service.py:45-126)."""
+one kernel launch here (kr_zncc).  The module-private helper `_zncc2` of the
+reference (zncc_service.py:45-126) has no counterpart in this package: nothing
+computes on the host here (its restatement lives in oracle/oracle.py, for the
+tests).  Host rasters are uploaded once per raster object and shared with
+KLT.match and the mutual-information service (core.image.device_full)."""
 from __future__ import annotations
 
 import logging
@@ -15,48 +18,53 @@ import torch
 from pandas import DataFrame, Series
 
 from karios_b200 import _native as N
+from karios_b200.core.image import device_full
 from karios_b200.matcher.klt import get_context
 
 logger = logging.getLogger(__name__)
 
 
-def _zncc2(img1, img2, u1, v1, u2, v2, n):
-    """ZNCC of two (2n+1)^2 windows centred at (row u, column v); raises like the
-    reference (ValueError for n < 0, IndexError outside the image) and returns
-    NaN for zero variance.  Evaluated on the GPU through kr_zncc when the window
-    is the production 43x43 one on chips; otherwise in NumPy (test helper)."""
-    if n < 0:
-        raise ValueError("Window half-size n must be non-negative")
-    h1, w1 = img1.shape
-    h2, w2 = img2.shape
-    if (u1 - n < 0 or u1 + n >= h1 or v1 - n < 0 or v1 + n >= w1
-            or u2 - n < 0 or u2 + n >= h2 or v2 - n < 0 or v2 + n >= w2):
-        raise IndexError("Patch window extends beyond image boundaries")
-    p1 = np.asarray(img1)[u1 - n:u1 + n + 1, v1 - n:v1 + n + 1].astype(np.float64)
-    p2 = np.asarray(img2)[u2 - n:u2 + n + 1, v2 - n:v2 + n + 1].astype(np.float64)
-    s1, s2 = p1.std(), p2.std()
-    if s1 == 0 or s2 == 0:
-        return np.nan
-    return float(np.mean(((p1 - p1.mean()) / s1) * ((p2 - p2.mean()) / s2)))
-
-
 def _raster_tensor(img, dev) -> torch.Tensor:
-    full = getattr(img, "device_array", None)
-    if full is not None:
-        return full
-    return N.to_device(img.array, dev)
+    return device_full(img, dev)
 
 
-def _score_inputs(df, monitored, reference):
-    """(ref tensor, mon tensor, [x0, y0, dx, dy] float32 device columns)."""
+def _score_inputs(df, monitored, reference, margin=28):
+    """(ref tensor, mon tensor, [x0, y0, dx, dy] float32 device columns), or None when no row
+    of `df` has both chips inside the rasters (the reference returns NaN for those rows
+    before it touches the pixel data, zncc_service.py:208-215 -- so the rasters are not
+    read, or uploaded, either).
+
+    The reference evaluates `round(series["x0"] + series["dx"])` on the row Series of
+    `df.apply(axis=1)`, whose dtype is the common dtype of the frame's columns: float32 for
+    the frames KLT.match yields, float64 as soon as the frame holds a float64 column.  The
+    kernel adds in float32; for a float64 frame the rounded monitored position is therefore
+    formed here in float64 and handed over as an exact integer displacement."""
+    cols = {c: df[c].to_numpy() for c in ("x0", "y0", "dx", "dy")}
+    host = np.empty((4, len(df)), np.float32)
+    common = np.result_type(*[df[c].dtype for c in df.columns]) if len(df.columns) else np.float32
+    for i, c in enumerate(("x0", "y0", "dx", "dy")):
+        host[i] = cols[c]
+    with np.errstate(invalid="ignore"):
+        if common != np.float32:
+            for i, (p, d) in enumerate((("x0", "dx"), ("y0", "dy"))):
+                p64 = cols[p].astype(np.float64)
+                x1 = np.rint(p64 + cols[d].astype(np.float64))
+                host[2 + i] = x1 - np.trunc(p64)
+                host[i] = np.trunc(p64)
+        ax, ay = np.trunc(host[0]), np.trunc(host[1])
+        bx, by = np.rint(host[0] + host[2]), np.rint(host[1] + host[3])
+        inside = ((ax - margin >= 0) & (ay - margin >= 0) & (bx - margin >= 0) & (by - margin >= 0)
+                  & (ax < reference.x_size - margin) & (ay < reference.y_size - margin)
+                  & (bx < monitored.x_size - margin) & (by < monitored.y_size - margin))
+    if not inside.any():
+        return None
     dev = torch.device("cuda", torch.cuda.current_device())
     mon = _raster_tensor(monitored, dev)
     ref = _raster_tensor(reference, dev)
     if mon.dtype != ref.dtype:
         raise N.KariosB200Error("monitored and reference rasters must share a dtype")
-    cols = [torch.from_numpy(np.array(df[c].to_numpy(np.float32), copy=True)).to(dev)
-            for c in ("x0", "y0", "dx", "dy")]
-    return ref, mon, cols
+    dcols = torch.from_numpy(host).to(dev)             # one H2D copy for the four columns
+    return ref, mon, [dcols[i] for i in range(4)]
 
 
 class ZNCCService:
@@ -73,10 +81,12 @@ class ZNCCService:
         if len(df) == 0:
             score = Series(np.empty(0, np.float64), index=df.index, dtype=np.float64)
         else:
-            ref, mon, cols = _score_inputs(df, monitored, reference)
-            ctx = get_context(64, 64, 1024)
-            z = ctx.zncc(ref, mon, *cols)
-            score = Series(z.cpu().numpy(), index=df.index, dtype=np.float64)
+            inp = _score_inputs(df, monitored, reference)
+            if inp is None:
+                score = Series(np.full(len(df), np.nan), index=df.index, dtype=np.float64)
+            else:
+                z = get_context(64, 64, 1024).zncc(*inp[:2], *inp[2])
+                score = Series(z.cpu().numpy(), index=df.index, dtype=np.float64)
         monitored.clear_cache()
         reference.clear_cache()
         logger.info("ZNCC computation finish")
@@ -90,9 +100,12 @@ class ZNCCService:
         if len(df) == 0:
             score = Series(np.empty(0, np.float64), index=df.index, dtype=np.float64)
         else:
-            ref, mon, cols = _score_inputs(df, monitored, reference)
-            mi = get_context(64, 64, 1024).mutual_info(ref, mon, *cols)
-            score = Series(mi[1].cpu().numpy(), index=df.index, dtype=np.float64)
+            inp = _score_inputs(df, monitored, reference)
+            if inp is None:
+                score = Series(np.full(len(df), np.nan), index=df.index, dtype=np.float64)
+            else:
+                mi = get_context(64, 64, 1024).mutual_info(*inp[:2], *inp[2])
+                score = Series(mi[1].cpu().numpy(), index=df.index, dtype=np.float64)
         monitored.clear_cache()
         reference.clear_cache()
         logger.info("NMI computation finish")

@@ -1,16 +1,42 @@
-"""Import the UNMODIFIED reference hot-path modules from /root/reference.
+"""Import the UNMODIFIED reference hot-path modules.
 
-Only usable in the build container (the reference tree does not travel to the
-GPU box); used by oracle/make_golden.py and by tests that pin the oracle when
-the tree is present.  Stubs follow SURVEY.md Appendix B: skimage / osgeo are
-absent, and karios/__init__.py (-> matplotlib) must not execute.
+TEST / MEASUREMENT INFRASTRUCTURE ONLY (never imported by karios_b200/).
+
+Source tree, in this order: $KARIOS_REFERENCE, /root/reference (build container
+only), oracle/_ref (byte-identical copies placed by oracle/vendor_ref.py during
+build(); they travel to the GPU box).  Used by oracle/make_golden.py, by the
+tests that pin the oracle, and by bench.py's CPU legs (`--impl reference`,
+`cpu_baseline`).  Stubs follow SURVEY.md Appendix B: skimage / osgeo are absent,
+and karios/__init__.py (-> matplotlib) must not execute.
 """
 import importlib
 import os
 import sys
 import types
 
-REF_ROOT = os.environ.get("KARIOS_REFERENCE", "/root/reference")
+_HERE = os.path.dirname(os.path.abspath(__file__))
+VENDORED = os.path.join(_HERE, "_ref")
+
+
+def _pick_root() -> str:
+    env = os.environ.get("KARIOS_REFERENCE")
+    if env:
+        return env
+    if os.path.isdir("/root/reference/karios/matcher"):
+        return "/root/reference"
+    return VENDORED
+
+
+REF_ROOT = _pick_root()
+
+
+def use_vendored() -> None:
+    """Point the loader at oracle/_ref (what the GPU box has) even when
+    /root/reference exists: bench.py runs the same files here and there."""
+    global REF_ROOT
+    if "karios.matcher.klt" in sys.modules:
+        return
+    REF_ROOT = VENDORED
 
 
 def available() -> bool:

@@ -304,3 +304,52 @@ def test_auto_ksize_and_polarity_match_reference(golden, name):
         off = [k for k in want if abs(scores[k] - want[k]) >= 1e-12]
         assert len(off) <= 1 and all(abs(scores[k] - want[k]) <= 0.02 for k in off), (label, off)
         assert list(best) == g[f"best_{label}"].tolist()
+
+
+# ---------------------------------------------------------------------------
+# The vendored reference (oracle/_ref, placed by oracle/vendor_ref.py during build()) that
+# bench.py's reference arm and cpu_baseline leg run on the GPU box.
+def test_vendored_reference_is_unmodified():
+    import hashlib
+    import os
+    from oracle import vendor_ref
+    if not vendor_ref.available():
+        if not os.path.isdir(os.path.join(vendor_ref.REF_SRC, "karios", "matcher")):
+            pytest.skip("no reference tree and no vendored copy here")
+        vendor_ref.vendor()
+    assert vendor_ref.available() and vendor_ref.verify() == []
+    if os.path.isdir(os.path.join(vendor_ref.REF_SRC, "karios", "matcher")):
+        for rel in vendor_ref.FILES:
+            src = os.path.join(vendor_ref.REF_SRC, rel)
+            if os.path.exists(src):
+                a = hashlib.sha256(open(src, "rb").read()).hexdigest()
+                b = hashlib.sha256(open(os.path.join(vendor_ref.DEST, rel), "rb").read()).hexdigest()
+                assert a == b, rel
+
+
+def test_reference_run_matches_restated_glue():
+    """oracle/ref_run.py (the unmodified KLT.match + compute_zncc, the bench's reference arm)
+    and oracle/cv2_path.py (the restated glue) give the same rows on a small pair with a
+    remainder tile."""
+    import logging
+    import os
+    import torch
+    from karios_b200 import synth
+    from oracle import cv2_path as P
+    from oracle import ref_run, vendor_ref
+    if not P.HAVE_CV2:
+        pytest.skip("cv2 not importable")
+    if not (vendor_ref.available() or os.path.isdir("/root/reference/karios/matcher")):
+        pytest.skip("no reference files")
+    logging.getLogger("karios").setLevel(logging.ERROR)
+    ref_t, mon_t = synth.make_pair(360, 500, seed=9)
+    to_np = lambda t: t.view(torch.int16).numpy().view(np.uint16)  # noqa: E731
+    ref, mon = to_np(ref_t), to_np(mon_t)
+    df, secs, how = ref_run.run_pair(mon, ref, None, maxCorners=300, tile_size=320)
+    tiles, total = P.match_scene(mon, ref, None, O.KLTConfiguration(maxCorners=300, tile_size=320))
+    assert total == len(df) > 300 and "unmodified" in how and secs > 0
+    for col, key in (("x0", "x0"), ("y0", "y0"), ("dx", "dx"), ("dy", "dy"), ("score", "score"), ("zncc_score", "zncc")):
+        want = np.concatenate([t[key] for t in tiles])
+        got = df[col].to_numpy()
+        assert np.array_equal(np.isnan(got), np.isnan(want))
+        assert np.allclose(got, want, rtol=0, atol=1e-12, equal_nan=True), col
