@@ -637,6 +637,8 @@ def cuda_arm(args):
             "gpu_launches": launches,      # kr_launch_count() over one timed batch (this rank)
             "clocks": sampler.summary(),
             "stats_last": {k: v for k, v in st.as_dict().items() if k.startswith("n_") or k == "nms_rounds"},
+            "corner_cut": {"est_cut_bits": int(st.est_cut_bits), "rows_skipped": int(st.rows_skipped),
+                           "row_pieces": ((size + 103) // 104) * size},
         }
         print(json.dumps(line), flush=True)
     sm.close()

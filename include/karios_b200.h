@@ -93,6 +93,8 @@ typedef struct {
     uint32_t two_tier_fallback; /* 1: it could not decide (flat image / list overflow) */
     uint32_t n_border_maxima;   /* two-tier: border / mask-edge pixels checked for the maximum */
     uint32_t n_exact;           /* two-tier: candidates confirmed in OpenCV's arithmetic */
+    uint32_t est_cut_bits;      /* two-tier: float bits of the running cut-off estimate tier 1 used (0: none) */
+    uint32_t rows_skipped;      /* two-tier: 104-pixel row pieces ruled out as a whole by that estimate */
 } kr_stats;
 
 /* SoA result rows of klt_tracker (klt.py:166-168), capacity >= max corners. */

@@ -14,7 +14,8 @@ import numpy as np
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "_lib", "libkarios_b200.so")
+# KR_LIB: another build of the same library (kernel A/B runs on one box, tools/build_variant.sh)
+LIB_PATH = os.environ.get("KR_LIB") or os.path.join(_HERE, "_lib", "libkarios_b200.so")
 
 KR_U8, KR_U16, KR_I16, KR_F32 = 0, 1, 2, 3
 KR_TAIL_NONE, KR_TAIL_AVX512 = 0, 32
@@ -51,7 +52,7 @@ class Stats(C.Structure):
                 ("nms_rounds", C.c_uint32), ("overflow", C.c_uint32),
                 ("select_incomplete", C.c_uint32), ("two_tier", C.c_uint32),
                 ("two_tier_fallback", C.c_uint32), ("n_border_maxima", C.c_uint32),
-                ("n_exact", C.c_uint32)]
+                ("n_exact", C.c_uint32), ("est_cut_bits", C.c_uint32), ("rows_skipped", C.c_uint32)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}

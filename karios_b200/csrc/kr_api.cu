@@ -260,6 +260,7 @@ KR_API int kr_ctx_create(int device, int max_w, int max_h, int max_corners, kr_c
     c->maxlist_cap = c->cand_cap / 4 > 65536 ? c->cand_cap / 4 : 65536;
     A(dev_alloc(&c->d_maxlist, c->maxlist_cap));
     A(dev_alloc(&c->d_hist, 4096));
+    A(dev_alloc(&c->d_ghist, 2048));            // >= FA_GBINS of kr_corner_fast.cu
     A(dev_alloc(&c->d_xy, c->cand_cap));
     A(dev_alloc(&c->d_state, c->cand_cap));
     A(dev_alloc(&c->d_next, c->cand_cap));
@@ -310,7 +311,7 @@ KR_API void kr_ctx_destroy(kr_ctx *c)
     if (!c) return;
     cudaFree(c->d_stats);
     for (int i = 0; i < 3; i++) cudaFree(c->d_lut[i]);
-    cudaFree(c->d_cand); cudaFree(c->d_keys_a); cudaFree(c->d_keys_b); cudaFree(c->d_hist);
+    cudaFree(c->d_cand); cudaFree(c->d_keys_a); cudaFree(c->d_keys_b); cudaFree(c->d_hist); cudaFree(c->d_ghist);
     cudaFree(c->d_maxlist);
     cudaFree(c->d_xy); cudaFree(c->d_state); cudaFree(c->d_next); cudaFree(c->d_cell_head);
     cudaFree(c->d_mask); cudaFree(c->d_lap[0]); cudaFree(c->d_lap[1]);
@@ -394,6 +395,8 @@ KR_API int kr_read_stats(kr_ctx *ctx, void *stream, kr_stats *o)
     o->two_tier_fallback = h.fast_fallback;
     o->n_border_maxima = h.n_maxlist;
     o->n_exact = h.n_exact;
+    o->est_cut_bits = h.cut_est_bits;
+    o->rows_skipped = h.fa_skipped;
     return KR_OK;
 }
 

@@ -50,6 +50,20 @@ constexpr float FA_K1 = 0.04f;                   // >= 1.5 x 64 d, d = 7000 * 2^
 constexpr float FA_K2 = 1.9073486328125e-6f;     // 2^-19 >= 13 * 2^-24 (products, formula, tier-1 float32)
 constexpr float FA_K0 = 0.001f;                  // second-order terms (225 d^2 ...)
 constexpr float FA_NEG_INF = -3.0e38f;   // 'nothing yet' for values that go through kr_f32_enc
+// Running cut (see approx_body): bins of the estimate histogram = float bits >> FA_GSHIFT (5 mantissa
+// bits, 3 % wide; est_bin), the estimate aims at FA_SAFETY x the number of candidates the selection needs,
+// a row piece is dropped when no pixel can reach the estimate minus FA_CUT_MARGIN (integer units;
+// >= 3 E(X) at the largest possible X = 2 * 225 * 1020^2, E = 1760 there), warps feed the histogram
+// during their first FA_EST_ROWS rows.
+// U is between K0 = 1e-3 and 2 * 225 * 1020^2 < 2^29 (integer units): biased exponents 117 .. 156,
+// FA_GGROUPS groups of 32 bins (one exponent each) from FA_GEXP0 on.
+constexpr int FA_GSHIFT = 18, FA_GEXP0 = 117, FA_GGROUPS = 40, FA_GBINS = 32 * FA_GGROUPS, FA_EST_ROWS = 8;
+__device__ __forceinline__ uint32_t est_bin(uint32_t ubits)
+{
+    const int b = (int)(ubits >> FA_GSHIFT) - (FA_GEXP0 << 5);
+    return (uint32_t)min(max(b, 0), FA_GBINS - 1);
+}
+constexpr float FA_SAFETY = 2.0f, FA_CUT_MARGIN = 8000.f;
 
 __device__ __forceinline__ int dp4a_us(uint32_t a, uint32_t b_s8x4)
 {
@@ -70,15 +84,96 @@ struct RowF { int hd[4], hs[4]; };
 // One response row: U (NaN where the pixel cannot be a candidate / the maximum:
 // masked out, outside the image, halo lane, X == 0) and the 3-wide maxima of the
 // masked lower bounds L' (-inf where masked out).
-struct RespRow { float U[4], H[4]; };
+struct RespRow { float U[4], H[4]; bool live; };     // live: the row was evaluated (warp-uniform)
 
 template <bool V> struct BoolTag { static constexpr bool value = V; };
+
+// Running cut, contribution of one warp (see approx_body): its candidates so far go into the estimate
+// histogram, then the row pieces they stand for are counted.  Out of line and free of warp
+// collectives on purpose: anything more in here (a shuffle, a lane-dependent branch that survives
+// inlining) makes ptxas guard every shuffle of the caller's row loop against divergence.
+__device__ __noinline__ void est_contribute(uint32_t *__restrict__ ghist, KrDevStats *st, const uint64_t *cbuf,
+                                            int n, int rows, int lane)
+{
+    // rows first, candidates second; the scanner reads the other way round (histogram, then rows):
+    // whatever it sees in the histogram is covered by the rows it counts, so a race can only make the
+    // estimated density -- and with it the estimate of the cut-off -- lower, which is the safe side
+    if (lane == 0) atomicAdd(&st->fa_rows, (uint32_t)rows);
+    __threadfence();
+    __syncwarp();
+    for (int k = lane; k < n; k += 32)
+        atomicAdd(&ghist[est_bin((uint32_t)(cbuf[k] >> 32))], 1u);
+}
+
+// Running cut, the scanner: one extra warp of the grid (block (0, 0), dispatched first) waits until
+// the histogram stands for `trigger_rows` row pieces -- or until every worker block is done, on
+// images too small to get there -- and turns it into the estimate of the cut-off: the lower edge of
+// the highest bin above which the sample holds need_per_row x rows candidates.  Nobody waits for it.
+__device__ __noinline__ void est_scanner(const uint32_t *ghist, KrDevStats *st, uint32_t trigger_rows,
+                                         float need_per_row, uint32_t n_workers, int lane)
+{
+    constexpr unsigned FULL = 0xffffffffu;
+    uint32_t rows = 0;
+    for (;;) {
+        uint32_t done = 0;
+        if (lane == 0) {
+            rows = *((volatile uint32_t *)&st->fa_rows);
+            done = *((volatile uint32_t *)&st->fa_done);
+        }
+        rows = __shfl_sync(FULL, rows, 0);
+        done = __shfl_sync(FULL, done, 0);
+        if (rows >= trigger_rows) break;
+        if (done >= n_workers) return;                       // small image: no estimate
+        __nanosleep(500);
+    }
+    uint32_t bits = 0;
+    for (int attempt = 0; attempt < 64; attempt++) {
+        const float need = need_per_row * (float)rows;
+        // bin 32 g + lane in v[g]: 40 independent, coalesced loads
+        uint32_t v[FA_GGROUPS];
+#pragma unroll
+        for (int g = 0; g < FA_GGROUPS; g++) v[g] = __ldcg(ghist + 32 * g + lane);
+        // groups from the top: the first one whose suffix count reaches the target
+        uint32_t suffix = 0, above = 0, mine = 0;
+        int gstar = -1;
+#pragma unroll
+        for (int g = FA_GGROUPS - 1; g >= 0; g--) {
+            const uint32_t tot = __reduce_add_sync(FULL, v[g]);
+            if (gstar < 0 && (float)(suffix + tot) >= need) { gstar = g; above = suffix; mine = v[g]; }
+            suffix += tot;
+        }
+        bits = 0;
+        uint32_t found = 0;
+        if (gstar >= 0) {
+            uint32_t incl = mine;                           // this lane's bin and the higher ones of the group
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t t = __shfl_down_sync(FULL, incl, o);
+                if (lane + o < 32) incl += t;
+            }
+            const unsigned ok = __ballot_sync(FULL, (float)(above + incl) >= need);     // lane 0 is always set
+            const int top = 31 - __clz(ok);
+            found = above + __shfl_sync(FULL, incl, top);
+            bits = (uint32_t)(32 * gstar + top + (FA_GEXP0 << 5)) << FA_GSHIFT;
+        }
+        // rows counted by now cover everything the histogram showed: the estimate stands if the
+        // count found still reaches the target at that row count, else look again
+        __threadfence();
+        uint32_t rows_now = 0;
+        if (lane == 0) rows_now = *((volatile uint32_t *)&st->fa_rows);
+        rows_now = __shfl_sync(FULL, rows_now, 0);
+        if (bits == 0 || (float)found >= need_per_row * (float)rows_now) break;
+        rows = rows_now;
+        bits = 0;
+    }
+    if (lane == 0 && bits) atomicExch(&st->cut_est_bits, bits);
+}
 
 template <bool BORDER, bool HAS_MASK>
 __device__ __forceinline__ void approx_body(
     const uint8_t *__restrict__ img, uint32_t pitch, const uint8_t *__restrict__ mask, uint32_t mpitch,
     int w, int h, uint64_t *__restrict__ cand, uint32_t cand_cap, uint64_t *__restrict__ maxlist,
-    uint32_t maxlist_cap, KrDevStats *st, int xs, int ys, int ye, uint4 *ring, uint64_t *cbuf, int lane)
+    uint32_t maxlist_cap, KrDevStats *st, int xs, int ys, int ye, uint4 *ring, uint64_t *cbuf, int lane,
+    uint32_t *__restrict__ ghist)
 {
     constexpr unsigned FULL = 0xffffffffu;
     const float NEG_INF = __int_as_float(0xff800000), QNAN = __int_as_float(0x7fc00000);
@@ -127,6 +222,36 @@ __device__ __forceinline__ void approx_body(
         ra.U[j] = rb.U[j] = rc.U[j] = QNAN;
         ra.H[j] = rb.H[j] = rc.H[j] = NEG_INF;
     }
+    ra.live = rb.live = rc.live = false;
+    // ---- running cut ----------------------------------------------------------------------
+    // Only the strongest ~2 maxCorners candidates survive the selection that follows, so most of
+    // the image cannot matter.  While a warp works through its first rows its candidates feed a
+    // global histogram; once enough rows of the whole grid are in (a stratified sample: the
+    // segments tile the image), the warp that crosses the mark turns the histogram into an
+    // estimate of the cut-off (aimed FA_SAFETY x too low) and publishes it.  From then on a row
+    // piece whose exact integer sums show that no pixel can reach the estimate -- lambda~ <=
+    // min(A, C) and lambda~ <= X/2 - |B| -- is dropped before the float bound, the local-maximum
+    // test and the emission.  Dropped pixels have U below the estimate, so they can neither be
+    // selected candidates nor the masked maximum, and they cannot veto a neighbour that matters
+    // (their L is below that neighbour's U); k_cutoff checks that the final cut-off is not below
+    // the estimate, else the call is re-run exactly (select_incomplete).  Which rows get dropped
+    // depends on timing; the corners do not.
+    int cut_i = ghist ? -1 : 0;                        // integer drop threshold; 0: none, < 0: not published yet
+    float cut_f = NEG_INF;                             // the same for single pixels: U below it is of no use
+    int n_dropped = 0;                                 // (both warp-uniform)
+    // (the estimate arrives through a warp reduction, not a shuffle: the compiler then knows the
+    // value -- and every branch on it -- to be warp-uniform and emits no convergence guards)
+    auto take_cut = [&]() {
+        uint32_t ce = 0;
+        if (lane == 0) ce = *((volatile const uint32_t *)&st->cut_est_bits);
+        ce = __reduce_max_sync(FULL, ce);
+        if (ce) {
+            const float c = __uint_as_float(ce) - FA_CUT_MARGIN;
+            cut_i = (c > FA_CUT_MARGIN) ? (int)c : 0;
+            if (cut_i > 0) cut_f = c;
+        }
+    };
+    if (ghist) take_cut();
     int cs[3][4];
 #pragma unroll
     for (int c = 0; c < 3; c++)
@@ -221,53 +346,59 @@ __device__ __forceinline__ void approx_body(
             bx[c][2] = mid + a1 + b2;
             bx[c][3] = mid + b3;
         }
-        // rows / columns outside the image hold mirrored data: no pixel there
-        const bool row_in = STEADY || ((r - 8) >= 0 && (r - 8) < h);
-        float L0[6];
+        bool live = true;
+        if (cut_i > 0) {
+            int v = INT_MIN;
 #pragma unroll
-        for (int j = 0; j < 4; j++) {
-            const int X = bx[0][j] + bx[2][j], T = bx[0][j] - bx[2][j];
-            const float fX = (float)X, fT = (float)T, fB = (float)bx[1][j];
-            const float rad = sqrt_approx(fmaf(fT * fT, 0.25f, fB * fB));
-            const float lam = fmaf(0.5f, fX, -rad);
-            // upper bound of sqrt(fX) (<= 6 % above): halve the exponent, keep the mantissa
-            const float sq = __int_as_float((__float_as_int(fX) >> 1) + 0x1fc00000);
-            const float E = fmaf(FA_K1, sq, fmaf(FA_K2, fX, FA_K0));
-            const float u = lam + E;
-            const bool mq = row_in && col_in[j] && (!HAS_MASK || ((mkq >> (8 * j)) & 255u) != 0);
-            L0[j + 1] = mq ? lam - E : NEG_INF;
-            // X == 0: every product of the window vanishes and so does OpenCV's value
-            N.U[j] = (mq && col_ok[j] && X != 0) ? u : QNAN;      // X >= 1 => u >= K0 > 0
+            for (int j = 0; j < 4; j++) {
+                const int a = bx[0][j], b = bx[1][j], c = bx[2][j];
+                v = max(v, min(min(a, c), ((a + c) >> 1) - abs(b)));
+            }
+            if (!out_lane) v = INT_MIN;                 // incomplete sums on the halo lanes
+            live = __any_sync(FULL, v >= cut_i);
         }
-        // (the outermost lanes have no neighbours for the 15-column sums: not pixels of this warp)
+        N.live = live;
+        if (live) {
+            // rows / columns outside the image hold mirrored data: no pixel there
+            const bool row_in = STEADY || ((r - 8) >= 0 && (r - 8) < h);
+            float L0[6];
+    #pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const int X = bx[0][j] + bx[2][j], T = bx[0][j] - bx[2][j];
+                const float fX = (float)X, fT = (float)T, fB = (float)bx[1][j];
+                const float rad = sqrt_approx(fmaf(fT * fT, 0.25f, fB * fB));
+                const float lam = fmaf(0.5f, fX, -rad);
+                // upper bound of sqrt(fX) (<= 6 % above): halve the exponent, keep the mantissa
+                const float sq = __int_as_float((__float_as_int(fX) >> 1) + 0x1fc00000);
+                const float E = fmaf(FA_K1, sq, fmaf(FA_K2, fX, FA_K0));
+                const float u = lam + E;
+                const bool mq = row_in && col_in[j] && (!HAS_MASK || ((mkq >> (8 * j)) & 255u) != 0);
+                L0[j + 1] = mq ? lam - E : NEG_INF;
+                // X == 0: every product of the window vanishes and so does OpenCV's value
+                N.U[j] = (mq && col_ok[j] && X != 0) ? u : QNAN;      // X >= 1 => u >= K0 > 0
+            }
+            // (the outermost lanes have no neighbours for the 15-column sums: not pixels of this warp)
+    #pragma unroll
+            for (int j = 0; j < 4; j++)
+                if (col_ok[j]) run_l = fmaxf(run_l, L0[j + 1]);
+            my_umax = fmaxf(my_umax, max3f(fmaxf(N.U[0], N.U[1]), N.U[2], N.U[3]));   // fmaxf drops NaN
+            L0[0] = __shfl_up_sync(FULL, L0[4], 1);
+            L0[5] = __shfl_down_sync(FULL, L0[1], 1);
+    #pragma unroll
+            for (int j = 0; j < 4; j++) N.H[j] = max3f(L0[j], L0[j + 1], L0[j + 2]);
+        } else {
+            n_dropped++;
 #pragma unroll
-        for (int j = 0; j < 4; j++)
-            if (col_ok[j]) run_l = fmaxf(run_l, L0[j + 1]);
-        my_umax = fmaxf(my_umax, max3f(fmaxf(N.U[0], N.U[1]), N.U[2], N.U[3]));   // fmaxf drops NaN
-        L0[0] = __shfl_up_sync(FULL, L0[4], 1);
-        L0[5] = __shfl_down_sync(FULL, L0[1], 1);
-#pragma unroll
-        for (int j = 0; j < 4; j++) N.H[j] = max3f(L0[j], L0[j + 1], L0[j + 2]);
+            for (int j = 0; j < 4; j++) { N.U[j] = QNAN; N.H[j] = NEG_INF; }
+        }
         // ---- row m = r - 9: restricted 3 x 3 maxima (NaN compares false) ----------
         const int m = r - 9;
         if (!STEADY && (m < ys || m >= ye)) return;         // warp-uniform
         const bool row_ok = STEADY || (m >= 1 && m <= h - 2);
+        if (!Q.live) return;                                // dropped row: no candidate in it
         bool rl[4];
 #pragma unroll
-        for (int j = 0; j < 4; j++) rl[j] = Q.U[j] >= max3f(P.H[j], Q.H[j], N.H[j]);
-        if ((m & 7) == 0) {                                 // share the lower bound between warps
-            float wl_ = run_l;
-            for (int o = 16; o > 0; o >>= 1) wl_ = fmaxf(wl_, __shfl_xor_sync(FULL, wl_, o));
-            uint32_t genc = 0;
-            if (lane == 0) {
-                const uint32_t mine = kr_f32_enc(wl_);
-                if (wl_ > pushed_l) genc = max(atomicMax(&st->lmax_enc, mine), mine);
-                else genc = *((volatile uint32_t *)&st->lmax_enc);
-            }
-            genc = __shfl_sync(FULL, genc, 0);
-            pushed_l = fmaxf(wl_, pushed_l);
-            run_l = fmaxf(wl_, kr_f32_dec_bits(genc, 0));
-        }
+        for (int j = 0; j < 4; j++) rl[j] = Q.U[j] >= fmaxf(max3f(P.H[j], Q.H[j], N.H[j]), cut_f);
         if constexpr (STEADY && !BORDER) {
             // Steady interior rows: Q.U is NaN on the halo lanes and every row / column is inside the
             // image, so rl[] already marks exactly this warp's possible candidates.  The first one of
@@ -368,27 +499,83 @@ __device__ __forceinline__ void approx_body(
         }
     };
 
+    // Every few rows: share the lower bound of the masked maximum between warps, pick the estimate
+    // of the cut-off up.
+    auto periodic = [&](int) {
+        float wl_ = run_l;
+        for (int o = 16; o > 0; o >>= 1) wl_ = fmaxf(wl_, __shfl_xor_sync(FULL, wl_, o));
+        uint32_t genc = 0;
+        if (lane == 0) {
+            const uint32_t mine = kr_f32_enc(wl_);
+            if (wl_ > pushed_l) genc = max(atomicMax(&st->lmax_enc, mine), mine);
+            else genc = *((volatile uint32_t *)&st->lmax_enc);
+        }
+        genc = __shfl_sync(FULL, genc, 0);
+        pushed_l = fmaxf(wl_, pushed_l);
+        run_l = fmaxf(wl_, kr_f32_dec_bits(genc, 0));
+        if (cut_i < 0) take_cut();
+    };
     // general rows until the steady range, whole triples of steady rows, general rows after it
     const int s_lo = max(ys + 9, 10), s_hi = min(r_last - 2, h - 3);       // steady: s_lo <= r <= s_hi
     int r = r_first;
     const BoolTag<false> general;
     const BoolTag<true> steady;
     for (; r <= r_last && r < s_lo; r += 3) {
+        periodic(r);
         step(general, r, fa, fb, fc, ra, rb, rc);
         if (r + 1 <= r_last) step(general, r + 1, fb, fc, fa, rb, rc, ra);
         if (r + 2 <= r_last) step(general, r + 2, fc, fa, fb, rc, ra, rb);
     }
-    for (; r + 2 <= s_hi; r += 3) {
-        step(steady, r, fa, fb, fc, ra, rb, rc);
-        step(steady, r + 1, fb, fc, fa, rb, rc, ra);
-        step(steady, r + 2, fc, fa, fb, rc, ra, rb);
+    // Steady rows, in two stretches of code.  While the estimate of the cut-off is not known
+    // (cut_i < 0): rounds of three triples with the periodic step in between, and the warp's one
+    // contribution to the estimate histogram after FA_EST_ROWS response rows (cut_i: -1 before it,
+    // -2 after).  Then the main loop, with nothing but the rows in it: interior strips have no more
+    // use for the periodic step (their lower bound of the maximum is pushed once, at the end), the
+    // strips on the left / right border keep it, it prunes their list of border-only maxima.
+    const int r_contrib = ys + 9 + FA_EST_ROWS;
+    while (cut_i < 0 && r + 2 <= s_hi) {
+        if (cut_i == -1 && r >= r_contrib) {                // (entries flushed meanwhile are lost to the
+            est_contribute(ghist, st, cbuf, ccount, min(r - 9 - ys, ye - ys), lane);   // estimate: safer)
+            cut_i = -2;
+        }
+        periodic(r);
+        const int r_stop = min(r + 9, s_hi - 1);
+        for (; r < r_stop; r += 3) {
+            step(steady, r, fa, fb, fc, ra, rb, rc);
+            step(steady, r + 1, fb, fc, fa, rb, rc, ra);
+            step(steady, r + 2, fc, fa, fb, rc, ra, rb);
+        }
+    }
+    if (cut_i == -1) {                                      // short segment: everything it had
+        est_contribute(ghist, st, cbuf, ccount, min(max(r - 9 - ys, 0), ye - ys), lane);
+        cut_i = -2;
+    }
+    if (BORDER) {
+        while (r + 2 <= s_hi) {
+            periodic(r);
+            const int r_stop = min(r + 9, s_hi - 1);
+            for (; r < r_stop; r += 3) {
+                step(steady, r, fa, fb, fc, ra, rb, rc);
+                step(steady, r + 1, fb, fc, fa, rb, rc, ra);
+                step(steady, r + 2, fc, fa, fb, rc, ra, rb);
+            }
+        }
+    } else {
+        for (; r + 2 <= s_hi; r += 3) {
+            step(steady, r, fa, fb, fc, ra, rb, rc);
+            step(steady, r + 1, fb, fc, fa, rb, rc, ra);
+            step(steady, r + 2, fc, fa, fb, rc, ra, rb);
+        }
     }
     for (; r <= r_last; r += 3) {
+        periodic(r);
         step(general, r, fa, fb, fc, ra, rb, rc);
         if (r + 1 <= r_last) step(general, r + 1, fb, fc, fa, rb, rc, ra);
         if (r + 2 <= r_last) step(general, r + 2, fc, fa, fb, rc, ra, rb);
     }
     __syncwarp();
+    if (lane == 0 && n_dropped) atomicAdd(&st->fa_skipped, (uint32_t)n_dropped);
+    if (lane == 0 && ghist) atomicAdd(&st->fa_done, 1u);
     if (ccount > 0) {
         uint32_t base = 0;
         if (lane == 0) base = atomicAdd(&st->n_cand, (uint32_t)ccount);
@@ -412,22 +599,33 @@ __global__ void __launch_bounds__(FA_WARPS * 32, BPS)
 k_eig_approx(const uint8_t *__restrict__ img, uint32_t pitch, const uint8_t *__restrict__ mask,
              uint32_t mpitch, int w, int h, uint64_t *__restrict__ cand, uint32_t cand_cap,
              uint64_t *__restrict__ maxlist, uint32_t maxlist_cap, KrDevStats *st, int seg, int aligned,
-             const unsigned long long *valid_count)
+             const unsigned long long *valid_count, uint32_t *__restrict__ ghist, uint32_t est_trigger_rows,
+             float est_need_per_row, uint32_t n_bands, uint32_t band_stride)
 {
     extern __shared__ __align__(16) unsigned char fa_smem[];
     const int lane = threadIdx.x, wid = 0;                       // FA_WARPS == 1
     uint4 *ring = reinterpret_cast<uint4 *>(fa_smem) + (size_t)wid * FA_RING_I4 + lane;   // [16][32]
     uint64_t *cbuf = reinterpret_cast<uint64_t *>(fa_smem + (size_t)FA_WARPS * FA_RING_I4 * 16) +
                      (size_t)wid * FA_CBUF;
+    // with the running cut the first row of the grid holds the scanner (block (0, 0)) and nothing else
+    const int by = ghist ? (int)blockIdx.y - 1 : (int)blockIdx.y;
+    if (by < 0) {
+        if (blockIdx.x == 0)
+            est_scanner(ghist, st, est_trigger_rows, est_need_per_row, gridDim.x * (gridDim.y - 1), lane);
+        return;
+    }
     const int xs = (blockIdx.x * FA_WARPS + wid) * FA_OUTW;
     if (xs >= w) return;
-    const int ys = blockIdx.y * seg, ye = min(ys + seg, h);
+    // bands are handed out with a stride (coprime to their number) instead of top to bottom, so
+    // that the blocks dispatched first -- the sample behind the estimate -- spread over the image
+    const int band = (int)(((unsigned)by * band_stride) % n_bands);
+    const int ys = band * seg, ye = min(ys + seg, h);
     const bool interior = aligned && (xs - FA_LEFT >= 0) && (xs - FA_LEFT + 128 <= w);
     // the context's auto mask with every pixel valid (the usual case) is no mask
     const bool use_mask = HAS_MASK && !(valid_count && *valid_count == (unsigned long long)w * h);
 #define FA_BODY(B, M)                                                                                  \
     approx_body<B, M>(img, pitch, mask, mpitch, w, h, cand, cand_cap, maxlist, maxlist_cap, st, xs, ys, \
-                      ye, ring, cbuf, lane)
+                      ye, ring, cbuf, lane, ghist)
     if (HAS_MASK && use_mask) {
         if (interior) FA_BODY(false, HAS_MASK); else FA_BODY(true, HAS_MASK);
     } else {
@@ -656,7 +854,7 @@ __global__ void k_commit_exact(KrDevStats *st)
 // Tier 1 + exact maximum.  Leaves the possible candidates in ctx->d_cand (keys in
 // integer units) and the exact masked maximum in d_stats->eig_max_enc.
 int krl_eig_fast(kr_ctx *ctx, const uint8_t *img, int64_t pitch, const uint8_t *mask, int64_t mask_pitch,
-                 int w, int h, float scale, int tail_start, cudaStream_t s)
+                 int w, int h, float scale, int tail_start, uint32_t target, cudaStream_t s)
 {
     // resident one-warp blocks per SM: 16 (128 registers per thread) or 20 (96), KR_EIG_BPS=4 / 5;
     // KR_EIG_SMEM_PAD adds unused shared memory per block (caps the residency, for tuning)
@@ -707,14 +905,32 @@ int krl_eig_fast(kr_ctx *ctx, const uint8_t *img, int64_t pitch, const uint8_t *
         if (cost < best_cost) { best_cost = cost; best_seg = sg; }
     }
     const int seg = cfg.seg >= 32 ? cfg.seg : best_seg;
-    dim3 grid(sb, (h + seg - 1) / seg);
     // the context's own auto mask: all-valid is known on the device (K1's count)
     const unsigned long long *valid = (mask && mask == ctx->d_mask) ? &ctx->d_stats->valid : nullptr;
+    // running cut (approx_body): the estimate is made once 1 % of the image's row pieces (at least
+    // 512 of them: small images never get there and run without a cut) are in the histogram; it
+    // aims at FA_SAFETY x target candidates, i.e. est_need_per_row per row piece of the sample
+    static const bool no_cut = getenv("KR_EIG_NOCUT") != nullptr;
+    const double total_rows = (double)sb * (double)h;
+    uint32_t *ghist = no_cut ? nullptr : ctx->d_ghist;
+    uint32_t trigger = (uint32_t)(total_rows / 100.0);
+    if (trigger < 512u) trigger = 512u;
+    const float need_per_row = (float)((double)FA_SAFETY * (double)target / total_rows);
+    if (ghist) KR_CUDA(cudaMemsetAsync(ghist, 0, FA_GBINS * sizeof(uint32_t), s));
+    const uint32_t n_bands = (uint32_t)((h + seg - 1) / seg);
+    uint32_t band_stride = 1;
+    if (ghist && n_bands > 4) {                     // ~0.38 n_bands, made coprime to n_bands
+        auto gcd = [](uint32_t a, uint32_t b) { while (b) { const uint32_t t = a % b; a = b; b = t; } return a; };
+        band_stride = (uint32_t)(0.381966 * n_bands) | 1u;
+        while (gcd(band_stride, n_bands) != 1) band_stride += 2;
+    }
+    dim3 grid(sb, n_bands + (ghist ? 1 : 0));
 #define FA_LAUNCH(M, B)                                                                                    \
     k_eig_approx<M, B><<<grid, FA_WARPS * 32, smem, s>>>(img, (uint32_t)pitch, mask, (uint32_t)mask_pitch, w, \
                                                         h, ctx->d_cand, (uint32_t)ctx->cand_cap,             \
                                                         ctx->d_maxlist, (uint32_t)ctx->maxlist_cap,          \
-                                                        ctx->d_stats, seg, aligned, valid)
+                                                        ctx->d_stats, seg, aligned, valid, ghist, trigger,     \
+                                                        need_per_row, n_bands, band_stride)
     if (mask) { if (bps == 20) FA_LAUNCH(true, 20); else FA_LAUNCH(true, 16); }
     else { if (bps == 20) FA_LAUNCH(false, 20); else FA_LAUNCH(false, 16); }
 #undef FA_LAUNCH

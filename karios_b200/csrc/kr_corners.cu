@@ -575,6 +575,9 @@ k_cutoff(KrDevStats *st, uint32_t *hist, uint32_t target, int select_all)
             if (c2 > cut) cut = c2;
         }
         st->cut_bits = cut;
+        // tier 1 dropped whole rows below its running estimate of this cut-off: the selection is
+        // complete only if the cut-off chosen here is not below that estimate
+        if (st->cut_est_bits && cut < st->cut_est_bits) st->fast_fallback = 1;
         st->cut_applied = (cut != st->thr_bits + 1) ? 1u : 0u;
         st->n_thr = total;
     }
@@ -867,6 +870,7 @@ __global__ void k_clear_counts(KrDevStats *st)
     st->lmax_enc = st->umax_enc = KR_ENC_NEG_INF;
     st->n_maxlist = st->n_exact = 0;
     st->cut_applied = st->fast_mode = st->fast_fallback = 0;
+    st->cut_est_bits = st->fa_rows = st->fa_skipped = st->fa_done = 0;
 }
 
 __global__ void k_set_fast_mode(KrDevStats *st) { st->fast_mode = 1; }
@@ -909,7 +913,8 @@ int krl_good_features(kr_ctx *ctx, const uint8_t *img, int64_t pitch, const uint
     if (fast) {
         k_set_fast_mode<<<1, 1, 0, s>>>(ctx->d_stats);
         KR_LAUNCH_CHECK();
-        KR_TRY(krl_eig_fast(ctx, img, pitch, mask, mask_pitch, w, h, scale, tail_start, s));
+        KR_TRY(krl_eig_fast(ctx, img, pitch, mask, mask_pitch, w, h, scale, tail_start,
+                            2u * (uint32_t)max_corners + 4096u, s));
     } else if (block == 15 && w >= 16 && h >= 16) {
         const size_t esm = (size_t)EC_WARPS * (EC_RING_F4 * 16 + EC_CBUF * 8);
         static bool ec_set = false;

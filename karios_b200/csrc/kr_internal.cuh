@@ -33,8 +33,12 @@ struct KrDevStats {
     uint32_t n_maxlist, n_exact;
     uint32_t cut_applied;               // the value cut-off dropped candidates above the threshold
     uint32_t fast_mode, fast_fallback;  // two-tier path in use / it cannot decide: re-run exactly
-    uint32_t pad[2];
+    uint32_t cut_est_bits;              // tier 1: running estimate of the value cut-off (0: none yet)
+    uint32_t fa_rows;                   // tier 1: warp-rows whose candidates are in the estimate histogram
     uint32_t nms_pending[16];           // multi-launch NMS: candidates left undecided by round r
+    uint32_t fa_skipped;                // tier 1: warp-rows ruled out as a whole by the running cut
+    uint32_t fa_done;                   // tier 1: worker blocks that have finished
+    uint32_t pad2[2];
 };
 
 struct kr_ctx {
@@ -50,6 +54,7 @@ struct kr_ctx {
     uint64_t *d_maxlist;    // two-tier K3: pixels that may hold the masked maximum
     int64_t maxlist_cap;
     uint32_t *d_hist;       // 4096-bin value histogram of the candidates
+    uint32_t *d_ghist;      // tier 1: 8192-bin histogram (float bits >> 18) of the first candidates seen
     uint32_t *d_xy;         // per selected candidate: x | y << 16
     uint8_t *d_state;       // NMS state per selected candidate
     int32_t *d_next;        // NMS cell lists: next pointer per candidate
@@ -214,7 +219,7 @@ int krl_mutual_info(const void *ref, int64_t rp, int rw, int rh, const void *mon
                     const float *dy, const float *score, float min_score, int n,
                     const uint32_t *d_count, double *out_studholme, double *out_nmi, cudaStream_t s);
 int krl_eig_fast(kr_ctx *ctx, const uint8_t *img, int64_t pitch, const uint8_t *mask, int64_t mask_pitch,
-                 int w, int h, float scale, int tail_start, cudaStream_t s);
+                 int w, int h, float scale, int tail_start, uint32_t target, cudaStream_t s);
 int krl_cand_hist_fast(kr_ctx *ctx, double quality, float scale, cudaStream_t s);
 int krl_exact_cands(kr_ctx *ctx, const uint8_t *img, int64_t pitch, int w, int h, float scale,
                     int tail_start, double quality, int expected, const uint64_t *sel, uint64_t *keys,

@@ -328,3 +328,48 @@ def test_exchange_header_written_on_the_device():
         assert m["n"] == total and abs(m["mean_dx"] - float(alldx.mean())) < 1e-9
     finally:
         sm.close()
+
+
+def test_running_cut_of_the_corner_response():
+    """Tier 1 of the corner response drops whole row pieces once its running estimate of the
+    selection cut-off is known (kr_corner_fast.cu).  Which rows are dropped depends on timing;
+    the corners must not: default mode against OpenCV's arithmetic at every pixel (corner mode 1)
+    on mid-size images of different character -- even texture, texture next to a flat half, few
+    strong corners in noise, a masked scene -- several times each."""
+    from karios_b200 import _native as N
+    from karios_b200 import synth
+    rng = np.random.default_rng(3)
+    ref_t, _ = synth.make_pair(2100, 3100, seed=8)
+    tex = O.laplacian(O.to_uint8(ref_t.view(torch.int16).numpy().view(np.uint16)), 7)
+    half = tex.copy()
+    half[:, 1500:] = 0
+    sparse = rng.integers(0, 12, tex.shape).astype(np.uint8)
+    for _ in range(300):
+        y, x = int(rng.integers(20, 2080)), int(rng.integers(20, 3080))
+        sparse[y:y + 9, x:x + 9] = 255
+    mask = (rng.random(tex.shape) > 0.4).astype(np.uint8)
+    mask[:, :700] = 0
+    cases = [("texture", tex, None, 3000), ("half flat", half, None, 3000), ("sparse", sparse, None, 200),
+             ("masked", tex, mask, 1500), ("texture, many corners", tex, None, 20000)]
+    ctx = N.Context(3100, 2100, 20000)
+    used = 0
+    try:
+        for name, img, m, mc in cases:
+            d_img = torch.from_numpy(img).cuda()
+            d_m = None if m is None else torch.from_numpy(m).cuda()
+            ctx.set_corner_mode(1)
+            want = ctx.good_features(d_img, d_m, mc, 0.1, 10, 15).cpu().numpy()
+            ctx.set_corner_mode(0)
+            for rep in range(3):
+                got = ctx.good_features(d_img, d_m, mc, 0.1, 10, 15).cpu().numpy()
+                st = ctx.read_stats()
+                assert np.array_equal(got, want), (name, rep, got.shape, want.shape)
+                print(f"{name}: corners {len(got)}, estimate bits {st.est_cut_bits:#x}, row pieces dropped "
+                      f"{st.rows_skipped}, candidates {st.n_candidates}, two-tier {st.two_tier}, "
+                      f"fallback {st.two_tier_fallback}")
+                used += int(st.rows_skipped > 0)
+                if name in ("texture", "texture, many corners"):
+                    assert st.two_tier_fallback == 0, "an even texture must not need the exact re-run"
+    finally:
+        ctx.close()
+    assert used > 0, "the running cut never engaged"

@@ -40,7 +40,9 @@ def test_struct_layouts_match_header():
     from karios_b200 import _native as N
     assert C.sizeof(N.KltConf) == 12 * 4 + 6 * 8                # 11 int32 + padding
     assert N.KltConf.compute_mi.offset == 40 and N.KltConf.quality_level.offset == 48
-    assert C.sizeof(N.Stats) == 4 * 8 + 8 + 4 + 12 * 4 + 4      # padded to 8
+    assert C.sizeof(N.Stats) == 4 * 8 + 8 + 4 + 14 * 4 + 4      # padded to 8
+    assert N.Stats.est_cut_bits.offset == 92 and N.Stats.rows_skipped.offset == 96
+    assert C.sizeof(N.UnitHeader) == 128 and N.UnitHeader.n.offset == 8 and N.UnitHeader.min_dx.offset == 48
     assert N.Stats.eig_max.offset == 40 and N.Stats.select_incomplete.offset == 72
     assert C.sizeof(N.Rows) == 8 * 8 + 8 and N.Rows.capacity.offset == 64
 
