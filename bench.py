@@ -555,6 +555,32 @@ def cuda_arm(args):
         def dropin_run(pairs_np):
             return sum(dropin_step(m, r) for m, r in pairs_np)
 
+        def dropin_step_imgs(mon_img, ref_img):
+            all_frame = pd.DataFrame()
+            for dataframe in KLT(conf).match(mon_img, ref_img, None):
+                cand = dataframe[dataframe["score"] >= 0.4]
+                dataframe["zncc_score"] = np.nan
+                z = zs.compute_zncc(cand, mon_img, ref_img)
+                dataframe.loc[cand.index, "zncc_score"] = z
+                all_frame = pd.concat([all_frame, dataframe])
+            return len(all_frame)
+
+        def dropin_run_prefetch(pairs_np):
+            """The same calls plus core.image.prefetch of the NEXT pair's rasters before the
+            current pair is matched (one added line in the caller's loop)."""
+            imgs = [(kimg.ArrayRaster(m), kimg.ArrayRaster(r)) for m, r in pairs_np]
+            total = 0
+            for im in imgs[0]:
+                kimg.prefetch(im)
+            for i, (mon_img, ref_img) in enumerate(imgs):
+                if i + 1 < len(imgs):
+                    for im in imgs[i + 1]:
+                        kimg.prefetch(im)
+                total += dropin_step_imgs(mon_img, ref_img)
+                kimg.release_device(mon_img)
+                kimg.release_device(ref_img)
+            return total
+
         pinned_np = [(as_np(m), as_np(r)) for m, r in host_pairs]
         seq_np = [pinned_np[i % len(pinned_np)] for i in range(n_e2e)]
         dropin_run(seq_np[:2])
@@ -569,6 +595,12 @@ def cuda_arm(args):
                       "api": "karios_b200.matcher.klt.KLT.match + ZNCCService.compute_zncc on NumPy rasters "
                              "(pinned-memory backed), pandas DataFrames out: the calls of karios/api/core.py:845-891",
                       "vs_scene_pipeline": round(dt_d / dt, 3)}
+        dropin_run_prefetch(seq_np[:3])
+        dt_pf, m4 = wall(lambda: dropin_run_prefetch(seq_np))
+        e2e_dropin["with_prefetch"] = {
+            "what": "the same calls + karios_b200.core.image.prefetch() of the next pair's rasters",
+            "ms_per_step": round(1e3 * dt_pf / len(seq_np), 3),
+            "scene_pairs_per_sec": round(world * len(seq_np) / dt_pf, 2), "vs_scene_pipeline": round(dt_pf / dt, 3)}
         if rank == 0 and world == 1:
             # the same through ordinary pageable NumPy arrays (what GDAL hands out today)
             pag = [(np.array(m, copy=True), np.array(r, copy=True)) for m, r in pinned_np[:1]]

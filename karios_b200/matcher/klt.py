@@ -24,7 +24,7 @@ import torch
 from pandas import DataFrame
 
 from karios_b200 import _native as N
-from karios_b200.core.image import device_full
+from karios_b200.core.image import device_full, remember_scores
 
 logger = logging.getLogger(__name__)
 
@@ -190,7 +190,7 @@ class KLT:
                     mask_t = mask_t.contiguous()
         ctx = get_context(x_size, y_size, int(conf.maxCorners))
         cap = int(conf.maxCorners) if conf.maxCorners > 0 else ctx._cap_unlimited(x_size, y_size)
-        rows = N.RowBuffers(cap, dev, with_zncc=False)
+        rows = N.RowBuffers(cap, dev, with_zncc=True)
         nd = (mon_img.no_data_value, ref_img.no_data_value)
 
         polarity = conf.laplacian_invert_polarity
@@ -225,11 +225,15 @@ class KLT:
         # klt.py:341-348.  "final": offsets added and rows sorted on the device;
         # "sorted": tile-local but already in (x0, y0) order; "raw": OpenCV order.
         state = points.attrs.pop("kr_state", "raw")
+        zncc = points.attrs.pop("kr_zncc", None)
         if state != "final":
             points["x0"] = points["x0"] + x_off
             points["y0"] = points["y0"] + y_off
         if state == "raw":
             points.sort_values(by=["x0", "y0"], inplace=True)
+        elif zncc is not None and polarity != "auto":
+            remember_scores(mon_img, ref_img,
+                            np.stack([points[c].to_numpy() for c in ("x0", "y0", "dx", "dy")]), zncc)
         logger.info("NbPoints(init/final): %s / %s", ninit, len(points.dx))
         return points
 
@@ -242,6 +246,11 @@ class KLT:
         kconf = N.make_conf(conf, invert_mon=invert, tail_mode=self._tail_mode)
         if conf.outliers_filtering:
             return self._track_once_unsorted(ctx, mon_t, ref_t, mask_t, win, rows, nd, invert, kconf)
+        # ZNCC of every row in the same launch sequence (the caller asks for it next,
+        # api/core.py:884-891; see core.image.remember_scores)
+        fused = rows.zncc is not None and mon_t.shape == ref_t.shape
+        if fused:
+            kconf.compute_zncc, kconf.zncc_min_score = 1, -3.0e38
         st = ctx.match_tile(mon_t, ref_t, mask_t, win, kconf, rows, nd[0], nd[1])
         if mask_t is None and st.valid == 0:
             logger.info("-- No valid pixels, skipping this tile")
@@ -253,6 +262,8 @@ class KLT:
         # the library added the window offset and sorted by (x0, y0); a host box has
         # window offset 0, so the tile offset is still to be added by the caller
         df.attrs["kr_state"] = "final" if (win[0] or win[1]) else "sorted"
+        if fused:
+            df.attrs["kr_zncc"] = rows.zncc[: st.n_kept].cpu().numpy()
         return df, int(st.n_corners), (kconf.ksize_mon, kconf.ksize_ref)
 
     def _track_once_unsorted(self, ctx, mon_t, ref_t, mask_t, win, rows, nd, invert, kconf):

@@ -18,7 +18,7 @@ import torch
 from pandas import DataFrame, Series
 
 from karios_b200 import _native as N
-from karios_b200.core.image import device_full
+from karios_b200.core.image import device_full, recall_scores
 from karios_b200.matcher.klt import get_context
 
 logger = logging.getLogger(__name__)
@@ -78,8 +78,11 @@ class ZNCCService:
         """ZNCC for each key point of `df` (columns x0, y0, dx, dy): Series with
         the index of `df`, NaN where not computable."""
         logger.info("Compute ZNCC for %s points", len(df))
+        known = recall_scores(monitored, reference, df) if len(df) else None
         if len(df) == 0:
             score = Series(np.empty(0, np.float64), index=df.index, dtype=np.float64)
+        elif known is not None:            # computed along with the matching of this tile
+            score = Series(known, index=df.index, dtype=np.float64)
         else:
             inp = _score_inputs(df, monitored, reference)
             if inp is None:

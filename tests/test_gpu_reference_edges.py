@@ -373,3 +373,72 @@ def test_running_cut_of_the_corner_response():
     finally:
         ctx.close()
     assert used > 0, "the running cut never engaged"
+
+
+def test_zncc_served_from_the_matching_pass():
+    """KLT.match leaves the ZNCC of the rows it yields (computed in the same launch sequence);
+    compute_zncc serves them only for bit-identical rows of that tile and computes otherwise --
+    the values are the same either way."""
+    from karios_b200.core import image as kimg
+    from karios_b200.core.configuration import KLTConfiguration
+    from karios_b200.core.image import ArrayRaster
+    from karios_b200.matcher.klt import KLT
+    from karios_b200.matcher.zncc_service import ZNCCService
+    ref, mon = _texture(420, 700, 29)
+    mon_img, ref_img = ArrayRaster(mon), ArrayRaster(ref)
+    zs = ZNCCService()
+    for df in KLT(KLTConfiguration(maxCorners=500, tile_size=400)).match(mon_img, ref_img, None):
+        cand = df[df["score"] >= 0.4]
+        assert kimg.recall_scores(mon_img, ref_img, cand) is not None          # known from the matching pass
+        served = zs.compute_zncc(cand, mon_img, ref_img)
+        fresh = zs.compute_zncc(cand, ArrayRaster(mon), ArrayRaster(ref))       # other raster objects: computed
+        assert list(served.index) == list(cand.index)
+        assert np.array_equal(np.isnan(served.to_numpy()), np.isnan(fresh.to_numpy()))
+        assert np.array_equal(np.nan_to_num(served.to_numpy()), np.nan_to_num(fresh.to_numpy()))
+        # rows that are not rows of the tile are computed, not served
+        moved = cand.copy()
+        moved["dx"] = moved["dx"] + np.float32(1.0)
+        assert kimg.recall_scores(mon_img, ref_img, moved) is None
+        renum = cand.reset_index(drop=True)
+        if len(renum) != len(df):
+            assert kimg.recall_scores(mon_img, ref_img, renum) is None
+        z2 = zs.compute_zncc(renum, mon_img, ref_img)
+        assert np.array_equal(np.nan_to_num(z2.to_numpy()), np.nan_to_num(served.to_numpy()))
+
+
+def test_prefetch_gives_the_same_rows():
+    """core.image.prefetch starts the upload on a copy stream; KLT.match / compute_zncc order
+    themselves after it and give what they give without it (one upload per raster either way)."""
+    from karios_b200.core import image as kimg
+    from karios_b200.core.configuration import KLTConfiguration
+    from karios_b200.core.image import ArrayRaster
+    from karios_b200.matcher.klt import KLT
+    from karios_b200.matcher.zncc_service import ZNCCService
+    pairs = [_texture(600, 900, s) for s in (41, 42, 43)]
+    conf = KLTConfiguration(maxCorners=700, tile_size=500)
+
+    def run(prefetch):
+        out = []
+        imgs = [(ArrayRaster(torch.from_numpy(m).pin_memory().numpy()), ArrayRaster(torch.from_numpy(r).pin_memory().numpy()))
+                for r, m in pairs]
+        before = kimg.uploads["count"]
+        if prefetch:
+            for im in imgs[0]:
+                kimg.prefetch(im)
+        for i, (mon_img, ref_img) in enumerate(imgs):
+            if prefetch and i + 1 < len(imgs):
+                for im in imgs[i + 1]:
+                    kimg.prefetch(im)
+            frames = list(KLT(conf).match(mon_img, ref_img, None))
+            df = pd.concat(frames)
+            z = ZNCCService().compute_zncc(df, mon_img, ref_img)
+            out.append((df, z))
+        assert kimg.uploads["count"] - before == 2 * len(pairs)
+        return out
+
+    a, b = run(False), run(True)
+    for (da, za), (db, zb) in zip(a, b):
+        assert len(da) == len(db) > 300
+        for c in ("x0", "y0", "dx", "dy", "score"):
+            assert np.array_equal(da[c].to_numpy(), db[c].to_numpy())
+        assert np.array_equal(np.nan_to_num(za.to_numpy()), np.nan_to_num(zb.to_numpy()))
