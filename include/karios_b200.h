@@ -280,6 +280,12 @@ KR_API int kr_histogram(const void *img, int64_t pitch, int dtype, int w, int h,
 KR_API int kr_count_valid(const void *img, int64_t pitch, int dtype, int w, int h, const uint8_t *mask,
                           int64_t mask_pitch, uint64_t *d_count, void *stream);
 
+/* Both of the above in ONE pass over the raster (the percentile histogram of _check_quality and
+ * the valid-pixel count of analyze_accuracy read the same monitored raster). */
+KR_API int kr_histogram_count(const void *img, int64_t pitch, int dtype, int w, int h, int lo, int shift,
+                              int nbins, uint64_t *hist, const uint8_t *mask, int64_t mask_pitch,
+                              uint64_t *d_count, void *stream);
+
 /* image.array[y0.astype(int), x0.astype(int)] as float64 (NaN outside the raster):
  * _filter_by_dn_values (karios/api/core.py:687-728), DEM altitudes (:1050-1053). */
 KR_API int kr_gather_points(const void *img, int64_t pitch, int dtype, int w, int h, const float *x0,

@@ -26,7 +26,7 @@ EXPORTS = [
     "kr_good_features", "kr_pyr_down", "kr_pyr_lk", "kr_klt_track", "kr_zncc", "kr_mutual_info",
     "kr_match_tile", "kr_auto_ksize", "kr_auto_ksize_scratch_bytes",
     "kr_set_profiling", "kr_read_stage_ms",
-    "kr_unit_header_write", "kr_cross_power", "kr_argmax_abs", "kr_shift_image", "kr_histogram", "kr_count_valid",
+    "kr_unit_header_write", "kr_cross_power", "kr_argmax_abs", "kr_shift_image", "kr_histogram", "kr_count_valid", "kr_histogram_count",
     "kr_gather_points",
 ]
 NUM_STAGES = 12
@@ -138,6 +138,7 @@ def load_library(path: str = LIB_PATH):
         L.kr_shift_image.argtypes = [vp, i64, vp, i64, i32, i32, i32, i32, i32, vp]
         L.kr_histogram.argtypes = [vp, i64, i32, i32, i32, i32, i32, i32, vp, vp]
         L.kr_count_valid.argtypes = [vp, i64, i32, i32, i32, vp, i64, vp, vp]
+        L.kr_histogram_count.argtypes = [vp, i64, i32, i32, i32, i32, i32, i32, vp, vp, i64, vp, vp]
         L.kr_gather_points.argtypes = [vp, i64, i32, i32, i32, vp, vp, i32, vp, vp]
         for name in EXPORTS:
             if name not in ("kr_last_error", "kr_ctx_destroy", "kr_version", "kr_launch_count",
@@ -539,6 +540,21 @@ def histogram(img: torch.Tensor, lo: int, hi: int, shift: int = 0) -> torch.Tens
                                 int(lo) + (start << shift), int(shift), nb, hist[start:].data_ptr(),
                                 _stream()))
     return hist
+
+
+def histogram_count(img: torch.Tensor, lo: int, hi: int, shift: int = 0, mask=None):
+    """histogram() and count_valid() in one pass (at most 8192 bins) -> (hist int64 tensor, count int)."""
+    lib = _require_cuda()
+    h, w = img.shape
+    n = ((int(hi) - int(lo)) >> shift) + 1
+    if n > 8192:
+        raise KariosB200Error("histogram_count: at most 8192 bins in one pass")
+    hist = torch.zeros(n, dtype=torch.int64, device=img.device)
+    out = torch.zeros(1, dtype=torch.int64, device=img.device)
+    _check(lib.kr_histogram_count(img.data_ptr(), _pitch(img), dtype_code(img), w, h, int(lo), int(shift), n,
+                                  hist.data_ptr(), mask.data_ptr() if mask is not None else None,
+                                  _pitch(mask) if mask is not None else 0, out.data_ptr(), _stream()))
+    return hist, int(out.item())
 
 
 def count_valid(img: torch.Tensor, mask=None) -> int:

@@ -305,44 +305,85 @@ def _dev_raster(img, dev):
     return N.to_device(img.array if hasattr(img, "array") else img, dev)
 
 
-def percentiles_2_98(raster) -> np.ndarray:
-    """np.nanpercentile(image.array, [2, 98]) of an integer raster
-    (KariosAPI._check_quality, karios/api/core.py:500-506): one device histogram,
-    then NumPy's 'linear' rule on the two order statistics."""
-    dev = torch.device("cuda", torch.cuda.current_device())
-    t = _dev_raster(raster, dev)
-    info = {torch.uint8: (0, 255), torch.uint16: (0, 65535), torch.int16: (-32768, 32767)}
-    if t.dtype not in info:
-        raise N.KariosB200Error("percentiles need an integer raster (uint8, uint16, int16)")
-    lo, hi = info[t.dtype]
-    # coarse pass over the whole value range (8 values per bin for 16 bits), then the
-    # few coarse bins that hold the wanted order statistics at full resolution
-    shift = 0 if t.dtype == torch.uint8 else 3
-    coarse = torch.cumsum(N.histogram(t, lo, hi, shift), 0).cpu().numpy()
+def _percentiles_from_hist(t, coarse_hist, lo, shift):
+    """NumPy's 'linear' 2nd / 98th percentile from the coarse histogram of raster `t` plus one
+    refinement pass (two when the coarse bins of the wanted order statistics are more than 8192
+    values apart) at full resolution."""
+    coarse = torch.cumsum(coarse_hist, 0).cpu().numpy()
     n = int(coarse[-1])
+    wanted = []
+    for q in (np.float64(2) / 100, np.float64(98) / 100):
+        virtual = n * q + (1 + q * (1 - 1 - 1)) - 1          # numpy _compute_virtual_index, alpha = beta = 1
+        prev = np.floor(virtual)
+        k0 = int(prev)
+        wanted.append((k0, min(k0 + 1, n - 1), virtual - prev))
+    ks = sorted({k for k0, k1, _ in wanted for k in (k0, k1)})
+    cbs = {k: int(np.searchsorted(coarse, k + 1, side="left")) for k in ks}
     fine = {}
+    if shift:
+        need = sorted(set(cbs.values()))
+        groups, cur = [], [need[0]]
+        for cb in need[1:]:                                    # coarse bins close enough share a pass
+            if ((cb - cur[0] + 1) << shift) <= 8192:
+                cur.append(cb)
+            else:
+                groups.append(cur)
+                cur = [cb]
+        groups.append(cur)
+        for g in groups:
+            base = lo + (g[0] << shift)
+            hist = N.histogram(t, base, lo + (g[-1] << shift) + (1 << shift) - 1).cpu().numpy()
+            for cb in g:
+                off = (cb - g[0]) << shift
+                fine[cb] = np.cumsum(hist[off: off + (1 << shift)])
 
     def value_at(k):                                   # k-th smallest value (0-based)
-        cb = int(np.searchsorted(coarse, k + 1, side="left"))
+        cb = cbs[k]
         if shift == 0:
             return lo + cb
-        if cb not in fine:
-            fine[cb] = torch.cumsum(N.histogram(t, lo + (cb << shift), lo + (cb << shift) + (1 << shift) - 1),
-                                    0).cpu().numpy()
         below = int(coarse[cb - 1]) if cb > 0 else 0
         return lo + (cb << shift) + int(np.searchsorted(fine[cb], k + 1 - below, side="left"))
 
     out = []
-    for q in (np.float64(2) / 100, np.float64(98) / 100):
-        virtual = n * q + (1 + q * (1 - 1 - 1)) - 1          # numpy _compute_virtual_index, alpha = beta = 1
-        prev = np.floor(virtual)
-        gamma = virtual - prev
-        k0 = int(prev)
-        k1 = min(k0 + 1, n - 1)
+    for k0, k1, gamma in wanted:
         a, b = np.float64(value_at(k0)), np.float64(value_at(k1))
         diff = b - a
         out.append(a + diff * gamma if gamma < 0.5 else b - diff * (1 - gamma))   # numpy _lerp
     return np.array(out)
+
+
+_INT_RANGES = {torch.uint8: (0, 255), torch.uint16: (0, 65535), torch.int16: (-32768, 32767)}
+
+
+def percentiles_2_98(raster) -> np.ndarray:
+    """np.nanpercentile(image.array, [2, 98]) of an integer raster
+    (KariosAPI._check_quality, karios/api/core.py:500-506): one coarse device histogram (8 values
+    per bin for 16 bits), one refinement pass over the coarse bins that hold the wanted order
+    statistics, then NumPy's 'linear' rule."""
+    dev = torch.device("cuda", torch.cuda.current_device())
+    t = _dev_raster(raster, dev)
+    if t.dtype not in _INT_RANGES:
+        raise N.KariosB200Error("percentiles need an integer raster (uint8, uint16, int16)")
+    lo, hi = _INT_RANGES[t.dtype]
+    shift = 0 if t.dtype == torch.uint8 else 3
+    return _percentiles_from_hist(t, N.histogram(t, lo, hi, shift), lo, shift)
+
+
+def scene_scan(raster, mask=None):
+    """(2nd / 98th percentiles, valid-pixel count) of one raster: the coarse histogram of
+    _check_quality (api/core.py:500-506) and np.count_nonzero under the mask (:285-290) come
+    from ONE pass over the raster (kr_histogram_count), the percentile refinement is a second."""
+    dev = torch.device("cuda", torch.cuda.current_device())
+    t = _dev_raster(raster, dev)
+    if t.dtype not in _INT_RANGES:
+        raise N.KariosB200Error("scene_scan needs an integer raster (uint8, uint16, int16)")
+    m = None if mask is None else _dev_raster(mask, dev)
+    if m is not None and m.dtype != torch.uint8:
+        m = (m != 0).to(torch.uint8)
+    lo, hi = _INT_RANGES[t.dtype]
+    shift = 0 if t.dtype == torch.uint8 else 3
+    hist, count = N.histogram_count(t, lo, hi, shift, m)
+    return _percentiles_from_hist(t, hist, lo, shift), count
 
 
 def check_quality(monitored_image, reference_image) -> dict:

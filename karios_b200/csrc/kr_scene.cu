@@ -126,6 +126,104 @@ k_histogram(const T *__restrict__ img, int64_t pitch, int w, int h, int lo, int 
         if (sh[i]) atomicAdd(&hist[i], (unsigned long long)sh[i]);
 }
 
+// One pass over an integer raster with 8-byte loads (rows 8-byte aligned): histogram of
+// (value - lo) >> shift into shared memory and / or the count of non-zero pixels under a mask.
+// Runs of equal bins inside a load are merged before the shared-memory atomic (neighbouring pixels
+// of a smooth raster share their coarse bin), four loads are in flight per thread.
+template <typename T, bool HIST, bool COUNT>
+__global__ void __launch_bounds__(256)
+k_scan8(const T *__restrict__ img, int64_t pitch, int w, int h, int lo, int shift, int nbins,
+        unsigned long long *__restrict__ hist, const uint8_t *__restrict__ mask, int64_t mpitch, int mask_vec,
+        unsigned long long *__restrict__ count)
+{
+    constexpr int VEC = 8 / (int)sizeof(T);
+    __shared__ uint32_t sh[HIST ? HIST_SPAN : 1];
+    if (HIST) {
+        for (int i = threadIdx.x; i < nbins; i += blockDim.x) sh[i] = 0;
+        __syncthreads();
+    }
+    const int nv = w / VEC;
+    unsigned long long nz = 0;
+    auto one = [&](uint2 raw, int x0, const uint8_t *mrow) {
+        T px[VEC];
+        memcpy(px, &raw, 8);
+        if (COUNT) {
+            uint8_t mk[VEC];
+            if (mrow) {
+                if (mask_vec) {
+                    if (VEC == 4) { const uint32_t m = *reinterpret_cast<const uint32_t *>(mrow + x0); memcpy(mk, &m, 4); }
+                    else { const uint2 m = *reinterpret_cast<const uint2 *>(mrow + x0); memcpy(mk, &m, 8); }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < VEC; i++) mk[i] = mrow[x0 + i];
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < VEC; i++) nz += (px[i] != (T)0 && (!mrow || mk[i] != 0)) ? 1u : 0u;
+        }
+        if (HIST) {
+            int cur = -1, cnt = 0;
+#pragma unroll
+            for (int i = 0; i < VEC; i++) {
+                const int d = (int)px[i] - lo;
+                int b = d >> shift;
+                if (d < 0 || b >= nbins) b = -1;
+                if (b != cur) {
+                    if (cur >= 0) atomicAdd(&sh[cur], (uint32_t)cnt);
+                    cur = b; cnt = 0;
+                }
+                cnt++;
+            }
+            if (cur >= 0) atomicAdd(&sh[cur], (uint32_t)cnt);
+        }
+    };
+    for (int y = blockIdx.x; y < h; y += gridDim.x) {
+        const char *rowb = (const char *)img + (int64_t)y * pitch;
+        const uint2 *row = reinterpret_cast<const uint2 *>(rowb);
+        const uint8_t *mrow = (COUNT && mask) ? mask + (int64_t)y * mpitch : nullptr;
+        int v = threadIdx.x;
+        for (; v + 3 * 256 < nv; v += 4 * 256) {
+            const uint2 a = __ldg(row + v), b = __ldg(row + v + 256), c = __ldg(row + v + 512), d = __ldg(row + v + 768);
+            one(a, v * VEC, mrow); one(b, (v + 256) * VEC, mrow); one(c, (v + 512) * VEC, mrow); one(d, (v + 768) * VEC, mrow);
+        }
+        for (; v < nv; v += 256) one(__ldg(row + v), v * VEC, mrow);
+        // the last w % VEC pixels of the row
+        const T *rowt = reinterpret_cast<const T *>(rowb);
+        for (int x = nv * VEC + threadIdx.x; x < w; x += 256) {
+            const T p = rowt[x];
+            if (COUNT) nz += (p != (T)0 && (!mrow || mrow[x] != 0)) ? 1u : 0u;
+            if (HIST) {
+                const int d = (int)p - lo, b = d >> shift;
+                if (d >= 0 && b < nbins) atomicAdd(&sh[b], 1u);
+            }
+        }
+    }
+    if (COUNT) {
+        for (int o = 16; o > 0; o >>= 1) nz += __shfl_xor_sync(0xffffffffu, nz, o);
+        if ((threadIdx.x & 31) == 0 && nz) atomicAdd(count, nz);
+    }
+    if (HIST) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < nbins; i += blockDim.x)
+            if (sh[i]) atomicAdd(&hist[i], (unsigned long long)sh[i]);
+    }
+}
+
+template <typename T>
+int launch_scan8(const void *img, int64_t pitch, int w, int h, int lo, int shift, int nbins, unsigned long long *hist,
+                 const uint8_t *mask, int64_t mpitch, unsigned long long *count, cudaStream_t s)
+{
+    constexpr int VEC = 8 / (int)sizeof(T);
+    const int grid = h < 148 * 8 ? h : 148 * 8;
+    const int mask_vec = mask && ((uintptr_t)mask % VEC == 0) && (mpitch % VEC == 0);
+    const T *p = (const T *)img;
+    if (hist && count) k_scan8<T, true, true><<<grid, 256, 0, s>>>(p, pitch, w, h, lo, shift, nbins, hist, mask, mpitch, mask_vec, count);
+    else if (hist) k_scan8<T, true, false><<<grid, 256, 0, s>>>(p, pitch, w, h, lo, shift, nbins, hist, mask, mpitch, mask_vec, count);
+    else k_scan8<T, false, true><<<grid, 256, 0, s>>>(p, pitch, w, h, lo, shift, nbins, hist, mask, mpitch, mask_vec, count);
+    KR_LAUNCH_CHECK();
+    return KR_OK;
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256)
 k_count_valid(const T *__restrict__ img, int64_t pitch, const uint8_t *__restrict__ mask, int64_t mpitch,
@@ -219,6 +317,14 @@ KR_API int kr_histogram(const void *img, int64_t pitch, int dtype, int w, int h,
     cudaStream_t s = (cudaStream_t)stream;
     const int grid = h < 148 * 4 ? h : 148 * 4;
     unsigned long long *hh = (unsigned long long *)hist;
+    if ((uintptr_t)img % 8 == 0 && pitch % 8 == 0) {
+        switch (dtype) {
+        case KR_U8: return launch_scan8<uint8_t>(img, pitch, w, h, lo, shift, nbins, hh, nullptr, 0, nullptr, s);
+        case KR_U16: return launch_scan8<uint16_t>(img, pitch, w, h, lo, shift, nbins, hh, nullptr, 0, nullptr, s);
+        case KR_I16: return launch_scan8<int16_t>(img, pitch, w, h, lo, shift, nbins, hh, nullptr, 0, nullptr, s);
+        default: return kr_set_error(KR_ERR_UNSUPPORTED, "histogram needs an integer raster (dtype %d)", dtype);
+        }
+    }
     switch (dtype) {
     case KR_U8: k_histogram<uint8_t><<<grid, 256, 0, s>>>((const uint8_t *)img, pitch, w, h, lo, shift, nbins, hh); break;
     case KR_U16: k_histogram<uint16_t><<<grid, 256, 0, s>>>((const uint16_t *)img, pitch, w, h, lo, shift, nbins, hh); break;
@@ -237,6 +343,10 @@ KR_API int kr_count_valid(const void *img, int64_t pitch, int dtype, int w, int 
     KR_CUDA(cudaMemsetAsync(d_count, 0, 8, s));
     const int grid = h < 148 * 8 ? h : 148 * 8;
     unsigned long long *o = (unsigned long long *)d_count;
+    if ((uintptr_t)img % 8 == 0 && pitch % 8 == 0 && dtype != KR_F32) {
+        if (dtype == KR_U8) return launch_scan8<uint8_t>(img, pitch, w, h, 0, 0, 1, nullptr, mask, mask_pitch, o, s);
+        return launch_scan8<uint16_t>(img, pitch, w, h, 0, 0, 1, nullptr, mask, mask_pitch, o, s);
+    }
     switch (dtype) {
     case KR_U8: k_count_valid<uint8_t><<<grid, 256, 0, s>>>((const uint8_t *)img, pitch, mask, mask_pitch, w, h, o); break;
     case KR_U16: case KR_I16: k_count_valid<uint16_t><<<grid, 256, 0, s>>>((const uint16_t *)img, pitch, mask, mask_pitch, w, h, o); break;
@@ -245,6 +355,27 @@ KR_API int kr_count_valid(const void *img, int64_t pitch, int dtype, int w, int 
     }
     KR_LAUNCH_CHECK();
     return KR_OK;
+}
+
+KR_API int kr_histogram_count(const void *img, int64_t pitch, int dtype, int w, int h, int lo, int shift,
+                              int nbins, uint64_t *hist, const uint8_t *mask, int64_t mask_pitch,
+                              uint64_t *d_count, void *stream)
+{
+    if (!img || !hist || !d_count || w < 1 || h < 1 || nbins < 1 || nbins > HIST_SPAN || shift < 0 || shift > 16)
+        return kr_set_error(KR_ERR_INVALID, "bad histogram arguments (1..%d bins per pass)", HIST_SPAN);
+    cudaStream_t s = (cudaStream_t)stream;
+    if ((uintptr_t)img % 8 == 0 && pitch % 8 == 0) {
+        KR_CUDA(cudaMemsetAsync(d_count, 0, 8, s));
+        unsigned long long *hh = (unsigned long long *)hist, *o = (unsigned long long *)d_count;
+        switch (dtype) {
+        case KR_U8: return launch_scan8<uint8_t>(img, pitch, w, h, lo, shift, nbins, hh, mask, mask_pitch, o, s);
+        case KR_U16: return launch_scan8<uint16_t>(img, pitch, w, h, lo, shift, nbins, hh, mask, mask_pitch, o, s);
+        case KR_I16: return launch_scan8<int16_t>(img, pitch, w, h, lo, shift, nbins, hh, mask, mask_pitch, o, s);
+        default: return kr_set_error(KR_ERR_UNSUPPORTED, "histogram needs an integer raster (dtype %d)", dtype);
+        }
+    }
+    KR_TRY(kr_histogram(img, pitch, dtype, w, h, lo, shift, nbins, hist, stream));
+    return kr_count_valid(img, pitch, dtype, w, h, mask, mask_pitch, d_count, stream);
 }
 
 KR_API int kr_gather_points(const void *img, int64_t pitch, int dtype, int w, int h, const float *x0,

@@ -560,6 +560,22 @@ def test_scene_scans():
         assert np.array_equal(got, O.percentiles_2_98(a)), (shape, got, O.percentiles_2_98(a))
     skew = (rng.gamma(2.0, 300.0, (500, 300))).astype(np.uint16)
     assert np.array_equal(api.percentiles_2_98(ArrayRaster(skew)), O.percentiles_2_98(skew))
+    # rows of a multiple of 8 bytes take the 8-byte-load kernel (k_scan8), others the scalar one;
+    # smooth rasters exercise the merged runs, the tail columns and the fused count
+    for shape, dt in (((301, 4100), np.uint16), ((300, 4103), np.uint16), ((129, 4104), np.uint8),
+                      ((200, 4108), np.int16)):
+        yy, xx = np.mgrid[0:shape[0], 0:shape[1]]
+        smooth = (1500 + 900 * np.sin(xx / 97.0) * np.cos(yy / 41.0) + rng.integers(0, 3, shape))
+        if dt == np.uint8:
+            smooth = smooth / 12
+        smooth = smooth.astype(dt)
+        smooth[::7, ::5] = 0
+        m = (rng.random(shape) > 0.3).astype(np.uint8)
+        assert np.array_equal(api.percentiles_2_98(ArrayRaster(smooth)), O.percentiles_2_98(smooth)), (shape, dt)
+        pct, cnt = api.scene_scan(ArrayRaster(smooth), ArrayRaster(m))
+        assert np.array_equal(pct, O.percentiles_2_98(smooth)) and cnt == O.count_valid_pixels(smooth, m)
+        assert api.count_valid_pixels(ArrayRaster(smooth)) == O.count_valid_pixels(smooth)
+        assert api.scene_scan(ArrayRaster(smooth))[1] == O.count_valid_pixels(smooth)
     q = api.check_quality(ArrayRaster(np.full((50, 50), 7, np.uint16)), ArrayRaster(skew))
     assert q["monitored"]["low_dynamic"] and not q["reference"]["low_dynamic"]
     mon = rng.integers(0, 5, (140, 150)).astype(np.uint16)

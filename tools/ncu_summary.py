@@ -24,6 +24,14 @@ KEYS = [
     ("sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active", "xu%"),
     ("smsp__issue_active.avg.pct_of_peak_sustained_active", "issue%"),
     ("l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "smem_conf"),
+    # shared-memory pipe: wavefronts (128 bytes each at full width) and their share of the pipe's peak
+    ("l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "smem_wavefronts"),
+    ("l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed", "smem_pipe%"),
+    ("l1tex__data_pipe_lsu_wavefronts_mem_shared_op_ld.sum.pct_of_peak_sustained_elapsed", "smem_ld%"),
+    ("l1tex__data_pipe_lsu_wavefronts_mem_shared_op_st.sum.pct_of_peak_sustained_elapsed", "smem_st%"),
+    ("lts__t_sectors.sum", "l2_sectors"),
+    ("lts__t_sector_hit_rate.pct", "l2_hit%"),
+    ("l1tex__t_sector_hit_rate.pct", "l1_hit%"),
     ("smsp__inst_executed.sum", "inst"),
 ]
 
@@ -44,6 +52,18 @@ def main(path):
             if k in idx and r[idx[k]] != "":
                 parts.append(f"{short}={r[idx[k]]}{units[idx[k]] if short in ('dur','dram_rd','dram_wr') else ''}")
         print("   ", "  ".join(parts))
+        try:        # derived: shared-memory and L2 throughput in bytes per second
+            dur_ns = float(r[idx["gpu__time_duration.sum"]].replace(",", ""))
+            if units[idx["gpu__time_duration.sum"]].strip() in ("us", "usecond"):
+                dur_ns *= 1e3
+            elif units[idx["gpu__time_duration.sum"]].strip() in ("ms", "msecond"):
+                dur_ns *= 1e6
+            wf = float(r[idx["l1tex__data_pipe_lsu_wavefronts_mem_shared.sum"]].replace(",", ""))
+            l2 = float(r[idx["lts__t_sectors.sum"]].replace(",", ""))
+            print(f"    shared memory {wf * 128 / dur_ns:.0f} GB/s at 128 B per wavefront "
+                  f"(peak 148 SMs x 128 B x 1.965 GHz = 37 230 GB/s), L2 {l2 * 32 / dur_ns:.0f} GB/s of sectors")
+        except Exception:  # noqa: BLE001
+            pass
         st = []
         for h in stall_cols:
             try:
