@@ -306,6 +306,12 @@ typedef struct {
 } kr_unit_header;
 KR_API int kr_unit_header_write(kr_ctx *ctx, kr_rows rows, kr_unit_header *d_out, void *stream);
 
+/* A host raster in ordinary (pageable) memory -- what GdalRasterImage.array / .read hand out
+ * (karios/core/image.py:300-388) -- to device memory: several host threads stage chunks through
+ * pinned buffers in parallel and overlap the DMA (one cudaMemcpy does this on one thread).
+ * Returns when the host memory has been read; `stream` is ordered after the last chunk. */
+KR_API int kr_upload_pageable(void *dst_device, const void *src_host, int64_t bytes, int device, void *stream);
+
 /* Measurement hooks (no reference counterpart).  With profiling on, kr_match_tile
  * brackets its stages with CUDA events on the caller's stream; after the stream
  * has been synchronised kr_read_stage_ms returns the KR_NUM_STAGES durations

@@ -26,7 +26,7 @@ EXPORTS = [
     "kr_good_features", "kr_pyr_down", "kr_pyr_lk", "kr_klt_track", "kr_zncc", "kr_mutual_info",
     "kr_match_tile", "kr_auto_ksize", "kr_auto_ksize_scratch_bytes",
     "kr_set_profiling", "kr_read_stage_ms",
-    "kr_unit_header_write", "kr_cross_power", "kr_argmax_abs", "kr_shift_image", "kr_histogram", "kr_count_valid", "kr_histogram_count",
+    "kr_unit_header_write", "kr_upload_pageable", "kr_cross_power", "kr_argmax_abs", "kr_shift_image", "kr_histogram", "kr_count_valid", "kr_histogram_count",
     "kr_gather_points",
 ]
 NUM_STAGES = 12
@@ -133,6 +133,7 @@ def load_library(path: str = LIB_PATH):
         L.kr_auto_ksize.argtypes = [vp, vp, i64, vp, i64, i32, i32, i32, vp, i64, i32, f64, i32, f64,
                                     C.POINTER(KltConf), C.POINTER(C.c_int32), i32, vp, i64, Rows, vp, vp]
         L.kr_unit_header_write.argtypes = [vp, Rows, vp, vp]
+        L.kr_upload_pageable.argtypes = [vp, vp, i64, i32, vp]
         L.kr_cross_power.argtypes = [vp, vp, i64, i32, vp]
         L.kr_argmax_abs.argtypes = [vp, i64, i32, vp, vp, vp]
         L.kr_shift_image.argtypes = [vp, i64, vp, i64, i32, i32, i32, i32, i32, vp]
@@ -175,7 +176,17 @@ def to_device(a, device) -> torch.Tensor:
             a = a.astype(np.uint8)
         t = torch.from_numpy(np.ascontiguousarray(a))
     if t.device.type != "cuda":
-        t = t.to(device, non_blocking=True)
+        dev = torch.device(device)
+        big = t.numel() * t.element_size() >= (8 << 20)
+        if big and t.is_contiguous() and dev.type == "cuda" and not t.is_pinned():
+            # ordinary host memory: parallel staged upload (kr_upload_pageable)
+            out = torch.empty(t.shape, dtype=t.dtype, device=dev)
+            _check(load_library().kr_upload_pageable(out.data_ptr(), t.data_ptr(), t.numel() * t.element_size(),
+                                                     dev.index if dev.index is not None else torch.cuda.current_device(),
+                                                     torch.cuda.current_stream(dev).cuda_stream))
+            t = out
+        else:
+            t = t.to(device, non_blocking=True)
     if t.dim() != 2:
         raise KariosB200Error(f"expected a 2-D raster, got shape {tuple(t.shape)}")
     if t.stride(1) != 1:

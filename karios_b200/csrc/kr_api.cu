@@ -5,7 +5,10 @@
 #include <stdlib.h>
 #include <math.h>
 #include <atomic>
+#include <mutex>
 #include <new>
+#include <thread>
+#include <vector>
 #include "kr_internal.cuh"
 
 static std::atomic<unsigned long long> g_launches{0};
@@ -327,6 +330,82 @@ KR_API int kr_unit_header_write(kr_ctx *ctx, kr_rows rows, kr_unit_header *d_out
     if (!rows.dx || !rows.dy || rows.capacity < 1) return kr_set_error(KR_ERR_INVALID, "incomplete rows");
     k_unit_header<<<1, 256, 0, (cudaStream_t)stream>>>(ctx->d_stats, rows, d_out);
     KR_LAUNCH_CHECK();
+    return KR_OK;
+}
+
+// ---- host rasters in ordinary (pageable) memory -> device ---------------------------------
+// cudaMemcpy from pageable memory goes through one staging copy on one thread (about 10 GB/s, a
+// 241 MB Sentinel-2 band in 20+ ms).  Here KR_UP_THREADS host threads each own a stream and two
+// pinned staging buffers and work through the chunks of the raster in turn: memcpy into a free
+// staging buffer, cudaMemcpyAsync from it, next chunk -- the staging copies of the threads run in
+// parallel and overlap the DMA.  Returns when the host memory has been read completely; the
+// caller's stream is ordered after the last chunk.
+namespace {
+constexpr int KR_UP_THREADS = 6;
+constexpr size_t KR_UP_CHUNK = 4u << 20;
+struct UpSlot { cudaStream_t s; void *buf[2]; cudaEvent_t ev[2]; cudaEvent_t done; };
+struct UpState { int device = -1; bool ok = false; UpSlot slot[KR_UP_THREADS]; std::mutex mu; };
+UpState g_up;
+
+int up_init(int device)
+{
+    if (g_up.ok && g_up.device == device) return KR_OK;
+    if (g_up.ok) return kr_set_error(KR_ERR_UNSUPPORTED, "kr_upload_pageable is bound to device %d", g_up.device);
+    KR_CUDA(cudaSetDevice(device));
+    for (int t = 0; t < KR_UP_THREADS; t++) {
+        UpSlot &u = g_up.slot[t];
+        KR_CUDA(cudaStreamCreateWithFlags(&u.s, cudaStreamNonBlocking));
+        for (int b = 0; b < 2; b++) {
+            KR_CUDA(cudaHostAlloc(&u.buf[b], KR_UP_CHUNK, cudaHostAllocDefault));
+            KR_CUDA(cudaEventCreateWithFlags(&u.ev[b], cudaEventDisableTiming));
+        }
+        KR_CUDA(cudaEventCreateWithFlags(&u.done, cudaEventDisableTiming));
+    }
+    g_up.device = device;
+    g_up.ok = true;
+    return KR_OK;
+}
+}  // namespace
+
+KR_API int kr_upload_pageable(void *dst_device, const void *src_host, int64_t bytes, int device, void *stream)
+{
+    if (!dst_device || !src_host || bytes < 0) return kr_set_error(KR_ERR_INVALID, "bad upload arguments");
+    if (bytes == 0) return KR_OK;
+    std::lock_guard<std::mutex> lock(g_up.mu);
+    KR_TRY(up_init(device));
+    cudaStream_t s = (cudaStream_t)stream;
+    // the destination may still be in use by work queued on the caller's stream
+    cudaEvent_t start;
+    KR_CUDA(cudaEventCreateWithFlags(&start, cudaEventDisableTiming));
+    KR_CUDA(cudaEventRecord(start, s));
+    const int64_t n_chunks = (bytes + (int64_t)KR_UP_CHUNK - 1) / (int64_t)KR_UP_CHUNK;
+    const int n_thr = (int)(n_chunks < KR_UP_THREADS ? n_chunks : KR_UP_THREADS);
+    std::atomic<int> failed{0};
+    auto work = [&](int t) {
+        if (cudaSetDevice(device) != cudaSuccess) { failed = 1; return; }
+        UpSlot &u = g_up.slot[t];
+        if (cudaStreamWaitEvent(u.s, start, 0) != cudaSuccess) { failed = 1; return; }
+        int b = 0;
+        for (int64_t c = t; c < n_chunks; c += n_thr, b ^= 1) {
+            const int64_t off = c * (int64_t)KR_UP_CHUNK;
+            const size_t n = (size_t)((bytes - off) < (int64_t)KR_UP_CHUNK ? (bytes - off) : (int64_t)KR_UP_CHUNK);
+            if (cudaEventSynchronize(u.ev[b]) != cudaSuccess) { failed = 1; return; }     // staging buffer free again
+            memcpy(u.buf[b], (const char *)src_host + off, n);
+            if (cudaMemcpyAsync((char *)dst_device + off, u.buf[b], n, cudaMemcpyHostToDevice, u.s) != cudaSuccess ||
+                cudaEventRecord(u.ev[b], u.s) != cudaSuccess) { failed = 1; return; }
+        }
+        if (cudaEventRecord(u.done, u.s) != cudaSuccess) failed = 1;
+    };
+    std::vector<std::thread> pool;
+    for (int t = 1; t < n_thr; t++) pool.emplace_back(work, t);
+    work(0);
+    for (auto &th : pool) th.join();
+    cudaEventDestroy(start);
+    if (failed) {
+        cudaGetLastError();
+        return kr_set_error(KR_ERR_CUDA, "kr_upload_pageable: a staging copy failed");
+    }
+    for (int t = 0; t < n_thr; t++) KR_CUDA(cudaStreamWaitEvent(s, g_up.slot[t].done, 0));
     return KR_OK;
 }
 

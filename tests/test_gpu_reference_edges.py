@@ -442,3 +442,25 @@ def test_prefetch_gives_the_same_rows():
         for c in ("x0", "y0", "dx", "dy", "score"):
             assert np.array_equal(da[c].to_numpy(), db[c].to_numpy())
         assert np.array_equal(np.nan_to_num(za.to_numpy()), np.nan_to_num(zb.to_numpy()))
+
+
+def test_parallel_upload_of_pageable_rasters():
+    """kr_upload_pageable (host threads staging chunks through pinned buffers) delivers the bytes
+    torch's own copy delivers: sizes around the chunk size, a raster-sized array, repeated use."""
+    from karios_b200 import _native as N
+    dev = torch.device("cuda", torch.cuda.current_device())
+    rng = np.random.default_rng(1)
+    for shape, dt in (((2048, 2049), np.uint16), ((4097, 1025), np.uint16), ((3000, 3001), np.float32),
+                      ((9000, 9011), np.uint16), ((4096, 2048), np.uint8)):
+        a = rng.integers(0, 60000, shape).astype(dt)
+        assert a.nbytes >= (8 << 20)
+        for _ in range(2):
+            got = N.to_device(a, dev)
+            torch.cuda.synchronize()
+            want = torch.from_numpy(a.view(np.int16) if dt == np.uint16 else a).cuda()
+            if dt == np.uint16:
+                got = got.view(torch.int16)
+            assert got.shape == want.shape and torch.equal(got, want), (shape, dt)
+    # small arrays and pinned memory keep the plain copy
+    small = rng.integers(0, 255, (100, 100)).astype(np.uint8)
+    assert torch.equal(N.to_device(small, dev), torch.from_numpy(small).cuda())
