@@ -12,6 +12,7 @@ of the next pair with the matching of the current one.
 """
 from __future__ import annotations
 
+import threading
 import time
 
 import numpy as np
@@ -216,12 +217,36 @@ def match_pair(mon, ref, mask, conf, confidence_threshold: float = 0.4, nodata=(
     mon_t, ref_t = N.to_device(mon, dev), N.to_device(ref, dev)
     mask_t = None if mask is None else N.to_device(mask, dev)
     h, w = mon_t.shape
+    sm = _cached_matcher(h, w, conf, confidence_threshold, tail_mode, dev)
+    tiles, _ = sm.match_device(mon_t, ref_t, mask_t, nodata)
+    return sm.to_frame(tiles)
+
+
+# match_pair keeps its workspace (a cudaMalloc of ~1.3 GB for an S2 tile costs ~80 ms, forty times
+# the matching): one SceneMatcher per thread, replaced when the scene size or the configuration changes
+_pair_tls = threading.local()
+
+
+def _cached_matcher(h, w, conf, confidence_threshold, tail_mode, dev):
+    key = (h, w, dev.index, float(confidence_threshold), int(tail_mode),
+           tuple(sorted((k, repr(v)) for k, v in vars(conf).items())))
+    ent = getattr(_pair_tls, "ent", None)
+    if ent is not None and ent[0] == key:
+        return ent[1]
+    if ent is not None:
+        ent[1].close()
+        _pair_tls.ent = None
     sm = SceneMatcher(h, w, conf, confidence_threshold, tail_mode, dev)
-    try:
-        tiles, _ = sm.match_device(mon_t, ref_t, mask_t, nodata)
-        return sm.to_frame(tiles)
-    finally:
-        sm.close()
+    _pair_tls.ent = (key, sm)
+    return sm
+
+
+def release_workspaces() -> None:
+    """Free the workspace match_pair keeps on this thread."""
+    ent = getattr(_pair_tls, "ent", None)
+    if ent is not None:
+        ent[1].close()
+        _pair_tls.ent = None
 
 
 class ScenePipeline:
