@@ -43,8 +43,10 @@ namespace {
 // compiler knows to be warp-uniform -- with several warps per block the strip index came from
 // threadIdx.x >> 5 and every shuffle was guarded by a convergence check (BRA.DIV + UMOV, 7 %
 // of the issued instructions).  FA_BLOCKS_PER_SM = resident warps per SM: 16 (128 registers
-// per thread) or 20 (96 registers, a few spills; KR_EIG_BPS=4 / 5 selects, 5 is the default).
-constexpr int FA_WARPS = 1, FA_BLOCKS_PER_SM = 20, FA_OUTW = 104, FA_LEFT = 12, FA_CBUF = 256;
+// per thread, no spills) or 20 (96 registers, a few spills); KR_EIG_BPS=4 / 5 selects.  20 was
+// the faster one before the running cut; with it 16 is (same box: 0.461 against 0.472 ms alone,
+// 1.280 against 1.326 ms per pair with six pairs in flight), so 16 is the default.
+constexpr int FA_WARPS = 1, FA_BLOCKS_PER_SM = 16, FA_OUTW = 104, FA_LEFT = 12, FA_CBUF = 256;
 constexpr int FA_RING_I4 = 16 * 32;              // uint4 per warp: 16 rows x 32 lanes of (Dx | Dy << 16) x 4
 constexpr float FA_K1 = 0.04f;                   // >= 1.5 x 64 d, d = 7000 * 2^-24 (Sobel rounding)
 constexpr float FA_K2 = 1.9073486328125e-6f;     // 2^-19 >= 13 * 2^-24 (products, formula, tier-1 float32)
@@ -862,7 +864,7 @@ int krl_eig_fast(kr_ctx *ctx, const uint8_t *img, int64_t pitch, const uint8_t *
     static const Cfg cfg = [] {
         Cfg c;
         const char *e = getenv("KR_EIG_BPS");
-        c.bps = (e && atoi(e) == 4) ? 16 : FA_BLOCKS_PER_SM;
+        c.bps = (e && atoi(e) == 5) ? 20 : ((e && atoi(e) == 4) ? 16 : FA_BLOCKS_PER_SM);
         const char *p = getenv("KR_EIG_SMEM_PAD");
         c.smem = (size_t)FA_WARPS * (FA_RING_I4 * 16 + FA_CBUF * 8) + (p ? (size_t)atoi(p) : 0);
         c.err = cudaFuncSetAttribute(k_eig_approx<true, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.smem);
