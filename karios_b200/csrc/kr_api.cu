@@ -98,37 +98,45 @@ __global__ void k_auto_copy(const kr_auto_result *r, AutoKs ks, const float *all
 
 
 static_assert(sizeof(kr_unit_header) == 128, "kr_unit_header is 128 bytes (karios_b200/sharding.py)");
-// count + dx / dy moments of the rows of the unit just matched (one block)
-__global__ void __launch_bounds__(256) k_unit_header(const KrDevStats *st, kr_rows rows, kr_unit_header *out)
+// count + dx / dy moments of the rows of the unit just matched (one block of 1024 threads:
+// float32 min / max are exact for float32 columns, the sums run in float64)
+__global__ void __launch_bounds__(1024) k_unit_header(const KrDevStats *st, kr_rows rows, kr_unit_header *out)
 {
-    __shared__ double sh[8][8];
+    __shared__ double ssum[32][4];
+    __shared__ float sext[32][4];
     uint32_t n = st->n_kept;
     if (n > (uint32_t)rows.capacity) n = rows.capacity;
-    double sx = 0, sy = 0, sxx = 0, syy = 0, mnx = INFINITY, mny = INFINITY, mxx = -INFINITY, mxy = -INFINITY;
+    double sx = 0, sy = 0, sxx = 0, syy = 0;
+    float mnx = INFINITY, mny = INFINITY, mxx = -INFINITY, mxy = -INFINITY;
     for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
-        const double dx = rows.dx[i], dy = rows.dy[i];
-        sx += dx; sy += dy; sxx += dx * dx; syy += dy * dy;
-        mnx = fmin(mnx, dx); mny = fmin(mny, dy); mxx = fmax(mxx, dx); mxy = fmax(mxy, dy);
+        const float fx = rows.dx[i], fy = rows.dy[i];
+        const double dx = fx, dy = fy;
+        sx += dx; sy += dy; sxx = fma(dx, dx, sxx); syy = fma(dy, dy, syy);
+        mnx = fminf(mnx, fx); mny = fminf(mny, fy); mxx = fmaxf(mxx, fx); mxy = fmaxf(mxy, fy);
     }
-    double v[8] = {sx, sy, sxx, syy, mnx, mny, mxx, mxy};
-    for (int o = 16; o; o >>= 1)
-        for (int k = 0; k < 8; k++) {
-            const double t = __shfl_xor_sync(0xffffffffu, v[k], o);
-            v[k] = k < 4 ? v[k] + t : (k < 6 ? fmin(v[k], t) : fmax(v[k], t));
-        }
+    for (int o = 16; o; o >>= 1) {
+        sx += __shfl_xor_sync(0xffffffffu, sx, o); sy += __shfl_xor_sync(0xffffffffu, sy, o);
+        sxx += __shfl_xor_sync(0xffffffffu, sxx, o); syy += __shfl_xor_sync(0xffffffffu, syy, o);
+        mnx = fminf(mnx, __shfl_xor_sync(0xffffffffu, mnx, o)); mny = fminf(mny, __shfl_xor_sync(0xffffffffu, mny, o));
+        mxx = fmaxf(mxx, __shfl_xor_sync(0xffffffffu, mxx, o)); mxy = fmaxf(mxy, __shfl_xor_sync(0xffffffffu, mxy, o));
+    }
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    if (lane == 0)
-        for (int k = 0; k < 8; k++) sh[warp][k] = v[k];
+    if (lane == 0) {
+        ssum[warp][0] = sx; ssum[warp][1] = sy; ssum[warp][2] = sxx; ssum[warp][3] = syy;
+        sext[warp][0] = mnx; sext[warp][1] = mny; sext[warp][2] = mxx; sext[warp][3] = mxy;
+    }
     __syncthreads();
     if (threadIdx.x == 0) {
-        for (int w = 1; w < 8; w++)
-            for (int k = 0; k < 8; k++)
-                sh[0][k] = k < 4 ? sh[0][k] + sh[w][k] : (k < 6 ? fmin(sh[0][k], sh[w][k]) : fmax(sh[0][k], sh[w][k]));
+        for (int w = 1; w < 32; w++) {
+            for (int k = 0; k < 4; k++) ssum[0][k] += ssum[w][k];
+            sext[0][0] = fminf(sext[0][0], sext[w][0]); sext[0][1] = fminf(sext[0][1], sext[w][1]);
+            sext[0][2] = fmaxf(sext[0][2], sext[w][2]); sext[0][3] = fmaxf(sext[0][3], sext[w][3]);
+        }
         out->n_rows = (int32_t)n;
         out->flags = (st->select_incomplete ? 1 : 0) | (st->overflow ? 2 : 0);
         out->n = (double)n;
-        out->sum_dx = sh[0][0]; out->sum_dy = sh[0][1]; out->sum_dx2 = sh[0][2]; out->sum_dy2 = sh[0][3];
-        out->min_dx = sh[0][4]; out->min_dy = sh[0][5]; out->max_dx = sh[0][6]; out->max_dy = sh[0][7];
+        out->sum_dx = ssum[0][0]; out->sum_dy = ssum[0][1]; out->sum_dx2 = ssum[0][2]; out->sum_dy2 = ssum[0][3];
+        out->min_dx = sext[0][0]; out->min_dy = sext[0][1]; out->max_dx = sext[0][2]; out->max_dy = sext[0][3];
         for (int k = 0; k < 6; k++) out->reserved[k] = 0.0;
     }
 }
@@ -328,7 +336,7 @@ KR_API int kr_unit_header_write(kr_ctx *ctx, kr_rows rows, kr_unit_header *d_out
 {
     if (!ctx || !d_out) return kr_set_error(KR_ERR_INVALID, "NULL argument");
     if (!rows.dx || !rows.dy || rows.capacity < 1) return kr_set_error(KR_ERR_INVALID, "incomplete rows");
-    k_unit_header<<<1, 256, 0, (cudaStream_t)stream>>>(ctx->d_stats, rows, d_out);
+    k_unit_header<<<1, 1024, 0, (cudaStream_t)stream>>>(ctx->d_stats, rows, d_out);
     KR_LAUNCH_CHECK();
     return KR_OK;
 }

@@ -745,7 +745,9 @@ bool lk_cache_enabled(int win)
 }
 size_t lk_smem_bytes(int win)
 {
-    return (size_t)LK_WARPS * ((size_t)win * (win + 1) * 8 + (lk_cache_enabled(win) ? (size_t)(win + 1 + 2 * LK_M) * 32 : 0));
+    // KR_LK_SMEM_PAD: unused shared memory per block (caps the resident warps per SM, for tuning)
+    static const size_t pad = getenv("KR_LK_SMEM_PAD") ? (size_t)atoi(getenv("KR_LK_SMEM_PAD")) : 0;
+    return (size_t)LK_WARPS * ((size_t)win * (win + 1) * 8 + (lk_cache_enabled(win) ? (size_t)(win + 1 + 2 * LK_M) * 32 : 0)) + pad;
 }
 
 int lk_prepare(KrLkArgs &a, size_t *smem)
