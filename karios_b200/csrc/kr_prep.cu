@@ -492,15 +492,24 @@ k_laplacian2(const T *__restrict__ img, int64_t pitch, int w, int h, const uint8
 // lane 1's word with the pixels mirrored (REFLECT_101), the last warp is shifted left to
 // end 4 columns right of the image and its lane 31 mirrors lane 30's word; rows are
 // reflected by index in the top / bottom segments only (ROWFAST elsewhere).
-constexpr int L4_WARPS = 4, L4_VALID = 120, L4_PF = 4, L4_LUT = 32768;
+constexpr int L4_WARPS = 4, L4_VALID = 120, L4_PF = 4;
 
 struct L4Raw { uint32_t x, y; };
 template <bool V> struct L4Tag { static constexpr bool value = V; };
 
-template <int K, typename T, bool ROWFAST, bool SLUT, bool EDGE>
+// ARITH: _to_uint8 of a 16-bit integer raster in integer arithmetic instead of the table.  The
+// reference's float64 expression ((v - mn) / (mx - mn) * 255).astype(uint8) (klt.py:47-48) equals
+// floor((v - mn) * 255 / R), R = mx - mn, for every 16-bit range: where the quotient is an exact
+// integer k the two roundings give fl(fl(k / 255) * 255) = k for all k <= 255, elsewhere it is at
+// least 1 / R >= 1.5e-5 away from an integer, against 6e-14 of float64 error (checked for every R
+// and every value, tests/test_oracle.py).  And floor(n * 255 / R) = (n * M) >> 32 with
+// M = ceil(2^32 * 255 / R) for n <= R <= 65535 when R >= 256 (M < 2^32; the excess n * (M R -
+// 255 * 2^32) stays below 2^32 / R of a step): ONE multiply-high per pixel, no table, no shared
+// memory, no bank conflicts (the table look-ups had the kernel at 62 % of the shared-memory pipe).
+template <int K, typename T, bool ROWFAST, bool ARITH, bool EDGE>
 __device__ __forceinline__ void lap4_body(const T *__restrict__ img, int64_t pitch, int h,
-                                          const uint8_t *__restrict__ lut, const uint8_t *slut,
-                                          uint32_t base2, uint32_t lim2, int invert,
+                                          const uint8_t *__restrict__ lut, int mn,
+                                          uint32_t base2, uint32_t magic, int invert,
                                           uint8_t *__restrict__ out, int64_t out_pitch, int lc, int oc,
                                           int edge, bool warp_edge, bool store_lane, int ys, int ye)
 {
@@ -550,10 +559,18 @@ __device__ __forceinline__ void lap4_body(const T *__restrict__ img, int64_t pit
     // ---- _to_uint8 of a raw row -> packed pairs ---------------------------------
     auto lut2 = [&](uint32_t pr) -> uint32_t {
         uint32_t t0, t1;
-        if (SLUT) {
-            const uint32_t a = __vminu2(pr - base2, lim2);
-            t0 = slut[a & 0xffffu];
-            t1 = slut[a >> 16];
+        if (ARITH) {
+            uint32_t n0, n1;
+            if ((T)-1 > (T)0) {                             // unsigned: every field >= mn, no borrow
+                const uint32_t d = pr - base2;
+                n0 = d & 0xffffu;
+                n1 = d >> 16;
+            } else {
+                n0 = (uint32_t)((int)(int16_t)(pr & 0xffffu) - mn);
+                n1 = (uint32_t)(((int)pr >> 16) - mn);
+            }
+            const uint32_t p = __byte_perm(__umulhi(n0, magic), __umulhi(n1, magic), 0x5410);
+            return invert ? 0x00ff00ffu - p : p;
         } else {
             t0 = __ldg(lut + (pr & 0xffffu));
             t1 = __ldg(lut + (pr >> 16));
@@ -653,27 +670,23 @@ k_laplacian4(const T *__restrict__ img, int64_t pitch, int w, int h, const uint8
              const KrDevStats *__restrict__ st, int slot, int invert, uint8_t *__restrict__ out,
              int64_t out_pitch, int seg)
 {
-    extern __shared__ __align__(16) unsigned char l4_smem[];
     constexpr int R = K / 2;
     constexpr bool U8 = sizeof(T) == 1;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    // value range of the raster -> table window in shared memory (unsigned 16-bit rasters)
-    bool use_slut = false;
-    uint32_t base2 = 0u, lim2 = 0u;
-    if (!U8 && ((T)-1 > (T)0)) {
-        const int mn = st->min_i[slot], mx = st->max_i[slot];
-        const int base = mn & ~3;
-        if (mn >= 0 && mx >= mn && mx < 65536 && mx - base < L4_LUT) {
-            use_slut = true;                                               // block-uniform
-            const int words = (mx - base) / 4 + 1;
-            const uint32_t *src = reinterpret_cast<const uint32_t *>(lut + base);
-            uint32_t *dst = reinterpret_cast<uint32_t *>(l4_smem);
-            for (int k = threadIdx.x; k < words; k += blockDim.x) dst[k] = __ldg(src + k);
-            base2 = (uint32_t)base * 0x00010001u;
-            lim2 = (uint32_t)(4 * words - 1) * 0x00010001u;
+    // 16-bit integer rasters with a value range of at least 256: arithmetic _to_uint8 (lap4_body);
+    // narrower ranges keep the (global, L1-resident) table
+    bool arith = false;                                                     // block-uniform
+    uint32_t base2 = 0u, magic = 0u;
+    int mn = 0;
+    if (!U8) {
+        mn = st->min_i[slot];
+        const int range = st->max_i[slot] - mn;
+        if (range >= 256 && range <= 65535) {
+            arith = true;
+            magic = (uint32_t)((((unsigned long long)255 << 32) + (unsigned)range - 1ull) / (unsigned)range);
+            base2 = ((uint32_t)mn & 0xffffu) * 0x00010001u;
         }
     }
-    __syncthreads();
     const int wx = blockIdx.x * L4_WARPS + wid;
     int x0 = wx * L4_VALID - 4;                       // first (virtual) column of the warp
     if (x0 + 4 >= w) return;
@@ -688,11 +701,11 @@ k_laplacian4(const T *__restrict__ img, int64_t pitch, int w, int h, const uint8
     // the first and the last block of a row hold the mirrored lanes (block-uniform choice)
     const bool edge_block = blockIdx.x == 0 || blockIdx.x == gridDim.x - 1;
 #define L4_BODY(RF, SL, ED)                                                                          \
-    lap4_body<K, T, RF, SL, ED>(img, pitch, h, lut, l4_smem, base2, lim2, invert, out, out_pitch, lc, \
+    lap4_body<K, T, RF, SL, ED>(img, pitch, h, lut, mn, base2, magic, invert, out, out_pitch, lc, \
                                 x0 + 4 * lane, edge, left || right, store_lane, ys, ye)
 #define L4_PICK(RF, SL)                                                                              \
     do { if (edge_block) L4_BODY(RF, SL, true); else L4_BODY(RF, SL, false); } while (0)
-    if (use_slut) {
+    if (arith) {
         if (rowfast) L4_PICK(true, true); else L4_PICK(false, true);
     } else {
         if (rowfast) L4_PICK(true, false); else L4_PICK(false, false);
@@ -751,7 +764,7 @@ int launch_lap4(kr_ctx *ctx, const void *img, int64_t pitch, int w, int h, int s
                 uint8_t *out, int64_t out_pitch, cudaStream_t s)
 {
     constexpr int R = K / 2;
-    const size_t smem = (sizeof(T) == 2 && ((T)-1 > (T)0)) ? (size_t)L4_LUT : 0;
+    const size_t smem = 0;
     struct Cfg { int bps, seg; cudaError_t err; };
     static const Cfg cfg = [smem] {
         Cfg c;

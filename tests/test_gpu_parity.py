@@ -95,8 +95,8 @@ def test_laplacian_dtypes_and_odd_shapes(N, ctx):
 
 def test_laplacian_four_pixel_path(N, ctx):
     """k_laplacian4 (4 pixels per lane; vector-aligned rows, w % 4 == 0, w >= 256, h >= 64):
-    table in shared memory (narrow value range) and in global memory (wide range, int16),
-    uint8 rasters, mirrored first / last lanes, reflected top / bottom rows, windows of a
+    _to_uint8 as one multiply-high per pixel (16-bit rasters with a value range >= 256, unsigned
+    and signed, with and without inversion) or through the table (narrower ranges), uint8 rasters, mirrored first / last lanes, reflected top / bottom rows, windows of a
     larger raster, every packed kernel size -- bit-exact against the oracle."""
     rng = np.random.default_rng(11)
     for shape in ((64, 256), (70, 260), (131, 492), (300, 1000), (517, 724)):
@@ -117,6 +117,17 @@ def test_laplacian_four_pixel_path(N, ctx):
         assert np.array_equal(ctx.u8_laplacian(dev(b), 7, invert=True).cpu().numpy(), O.laplacian(255 - b, 7))
         ai = rng.integers(-3000, 9000, shape).astype(np.int16)
         assert np.array_equal(ctx.u8_laplacian(dev(ai), 7).cpu().numpy(), O.laplacian(O.to_uint8(ai), 7)), shape
+    # value ranges either side of the switch between the table and the multiply-high (256), the
+    # extremes of both 16-bit types, inverted polarity
+    for lo, hi, dt in ((500, 510, np.uint16), (7, 262, np.uint16), (7, 263, np.uint16), (7, 264, np.uint16),
+                       (0, 65535, np.uint16), (65000, 65535, np.uint16), (-32768, 32767, np.int16),
+                       (-300, -40, np.int16), (-300, -44, np.int16), (-5, 12000, np.int16)):
+        a = rng.integers(lo, hi + 1, (96, 512)).astype(dt)
+        a[0, 0], a[-1, -1] = lo, hi
+        for inv in (False, True):
+            u8 = O.to_uint8(a)
+            got = ctx.u8_laplacian(dev(a), 7, invert=inv).cpu().numpy()
+            assert np.array_equal(got, O.laplacian(255 - u8 if inv else u8, 7)), (lo, hi, dt, inv)
     # aligned window of a larger raster (tile of a resident scene) and a value range that
     # straddles a 4-aligned table base
     big = rng.integers(1003, 1003 + 32000, (400, 1024)).astype(np.uint16)

@@ -353,3 +353,29 @@ def test_reference_run_matches_restated_glue():
         got = df[col].to_numpy()
         assert np.array_equal(np.isnan(got), np.isnan(want))
         assert np.allclose(got, want, rtol=0, atol=1e-12, equal_nan=True), col
+
+
+def test_to_uint8_is_an_integer_division():
+    """The arithmetic _to_uint8 of the 4-pixel Laplacian kernel (kr_prep.cu: lap4_body, ARITH):
+    ((v - mn) / (mx - mn) * 255).astype(uint8) in float64 == (v - mn) * 255 // (mx - mn), and for
+    ranges >= 256 == ((v - mn) * ceil(2^32 * 255 / R)) >> 32 with a multiplier below 2^32.  A sample
+    of ranges here (all of them: tools/verify_to_uint8_integer.py), unsigned and signed."""
+    rng = np.random.default_rng(5)
+    ranges = sorted(set([1, 2, 3, 5, 15, 17, 51, 85, 254, 255, 256, 257, 510, 765, 1020, 3000, 4095, 4096,
+                         32767, 32768, 65025, 65534, 65535] + [int(r) for r in rng.integers(1, 65536, 300)]))
+    for R in ranges:
+        for mn in {0, int(rng.integers(0, 65536 - R)), 65535 - R}:
+            v = np.arange(mn, mn + R + 1, dtype=np.uint16)
+            want = ((v - float(mn)) / (float(mn + R) - float(mn)) * 255).astype(np.uint8)
+            n = v.astype(np.int64) - mn
+            assert np.array_equal(want, (n * 255) // R), (R, mn)
+            assert np.array_equal(want, O.to_uint8(v)), (R, mn)
+            if R >= 256:
+                M = -(-(255 << 32) // R)
+                assert M < 2 ** 32 and np.array_equal(want, (n * M) >> 32), (R, mn)
+    for R in (300, 5000, 40000, 65535):                                   # int16 rasters
+        mn = -32768 if R == 65535 else int(rng.integers(-32768, 32767 - R))
+        v = np.arange(mn, mn + R + 1, dtype=np.int32).astype(np.int16)
+        want = ((v - float(mn)) / (float(mn + R) - float(mn)) * 255).astype(np.uint8)
+        n = v.astype(np.int64) - mn
+        assert np.array_equal(want, (n * (-(-(255 << 32) // R))) >> 32)
