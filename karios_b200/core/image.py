@@ -25,7 +25,14 @@ uploads = {"count": 0, "bytes": 0}        # host -> device raster copies made so
 
 
 _COPY_STREAMS: dict = {}           # device index -> stream of the prefetch copies
-_PENDING: dict = {}                # id(tensor) -> event of the prefetch copy that fills it
+
+
+class _Entry:
+    """A cached device copy and, while its prefetch copy may still be running, that copy's event."""
+    __slots__ = ("tensor", "event")
+
+    def __init__(self, tensor, event=None):
+        self.tensor, self.event = tensor, event
 
 
 def prefetch(img, device=None, as_mask: bool = False) -> None:
@@ -58,28 +65,27 @@ def prefetch(img, device=None, as_mask: bool = False) -> None:
         ev.record(stream)
     uploads["count"] += 1
     uploads["bytes"] += t.numel() * t.element_size()
-    _PENDING[id(t)] = ev
-    _store(img, key, t)
+    _store(img, key, t, ev)
 
 
-def _store(img, key, t) -> None:
+def _store(img, key, t, event=None) -> None:
     try:
         with _CACHE_LOCK:
-            _CACHE.setdefault(img, {})[key] = t
+            _CACHE.setdefault(img, {})[key] = _Entry(t, event)
             _CACHE_ORDER[:] = [r for r in _CACHE_ORDER if r() is not None and r() is not img]
             _CACHE_ORDER.append(weakref.ref(img))
             while len(_CACHE_ORDER) > _CACHE_MAX:
                 old = _CACHE_ORDER.pop(0)()
                 if old is not None:
-                    for tt in (_CACHE.pop(old, None) or {}).values():
-                        _PENDING.pop(id(tt), None)
+                    _CACHE.pop(old, None)
     except TypeError:
         pass
 
 
-def _ready(t: torch.Tensor) -> torch.Tensor:
-    """Order the current stream after the prefetch copy of `t`, if one is still pending."""
-    ev = _PENDING.pop(id(t), None)
+def _ready(ent: "_Entry") -> torch.Tensor:
+    """Order the current stream after the prefetch copy of the entry, if one is still pending."""
+    ev, ent.event = ent.event, None
+    t = ent.tensor
     if ev is not None:
         cur = torch.cuda.current_stream(t.device)
         cur.wait_event(ev)

@@ -352,13 +352,13 @@ namespace {
 constexpr int KR_UP_THREADS = 6;
 constexpr size_t KR_UP_CHUNK = 4u << 20;
 struct UpSlot { cudaStream_t s; void *buf[2]; cudaEvent_t ev[2]; cudaEvent_t done; };
-struct UpState { int device = -1; bool ok = false; UpSlot slot[KR_UP_THREADS]; std::mutex mu; };
-UpState g_up;
+constexpr int KR_UP_MAX_DEVICES = 32;
+struct UpState { bool ok = false; UpSlot slot[KR_UP_THREADS]; std::mutex mu; };
+UpState g_up_dev[KR_UP_MAX_DEVICES];            // one set of streams / staging buffers per device
 
-int up_init(int device)
+int up_init(UpState &g_up, int device)
 {
-    if (g_up.ok && g_up.device == device) return KR_OK;
-    if (g_up.ok) return kr_set_error(KR_ERR_UNSUPPORTED, "kr_upload_pageable is bound to device %d", g_up.device);
+    if (g_up.ok) return KR_OK;
     KR_CUDA(cudaSetDevice(device));
     for (int t = 0; t < KR_UP_THREADS; t++) {
         UpSlot &u = g_up.slot[t];
@@ -369,7 +369,6 @@ int up_init(int device)
         }
         KR_CUDA(cudaEventCreateWithFlags(&u.done, cudaEventDisableTiming));
     }
-    g_up.device = device;
     g_up.ok = true;
     return KR_OK;
 }
@@ -379,8 +378,10 @@ KR_API int kr_upload_pageable(void *dst_device, const void *src_host, int64_t by
 {
     if (!dst_device || !src_host || bytes < 0) return kr_set_error(KR_ERR_INVALID, "bad upload arguments");
     if (bytes == 0) return KR_OK;
+    if (device < 0 || device >= KR_UP_MAX_DEVICES) return kr_set_error(KR_ERR_INVALID, "bad device %d", device);
+    UpState &g_up = g_up_dev[device];
     std::lock_guard<std::mutex> lock(g_up.mu);
-    KR_TRY(up_init(device));
+    KR_TRY(up_init(g_up, device));
     cudaStream_t s = (cudaStream_t)stream;
     // the destination may still be in use by work queued on the caller's stream
     cudaEvent_t start;
