@@ -14,8 +14,7 @@ import logging
 import numpy as np
 from pandas import DataFrame, Series
 
-from karios_b200.matcher.klt import get_context
-from karios_b200.matcher.zncc_service import _score_inputs
+from karios_b200.matcher.zncc_service import mutual_info_pair
 
 logger = logging.getLogger(__name__)
 
@@ -34,12 +33,8 @@ class MutualInfoService:
         if len(df) == 0:
             score = Series(np.empty(0, np.float64), index=df.index, dtype=np.float64)
         else:
-            inp = _score_inputs(df, monitored, reference)
-            if inp is None:
-                score = Series(np.full(len(df), np.nan), index=df.index, dtype=np.float64)
-            else:
-                mi = get_context(64, 64, 1024).mutual_info(*inp[:2], *inp[2])
-                score = Series(mi[0].cpu().numpy(), index=df.index, dtype=np.float64)
+            pair = mutual_info_pair(df, monitored, reference)
+            score = Series(np.full(len(df), np.nan) if pair is None else pair[0], index=df.index, dtype=np.float64)
         monitored.clear_cache()
         reference.clear_cache()
         logger.info("Mutual information computation finish")

@@ -18,7 +18,7 @@ import torch
 from pandas import DataFrame, Series
 
 from karios_b200 import _native as N
-from karios_b200.core.image import device_full, recall_scores
+from karios_b200.core.image import device_full, recall_mi, recall_scores, remember_mi
 from karios_b200.matcher.klt import get_context
 
 logger = logging.getLogger(__name__)
@@ -64,7 +64,26 @@ def _score_inputs(df, monitored, reference, margin=28):
     if mon.dtype != ref.dtype:
         raise N.KariosB200Error("monitored and reference rasters must share a dtype")
     dcols = torch.from_numpy(host).to(dev)             # one H2D copy for the four columns
-    return ref, mon, [dcols[i] for i in range(4)]
+    return ref, mon, [dcols[i] for i in range(4)], host
+
+
+def mutual_info_pair(df, monitored, reference):
+    """[2, n] float64 -- row 0: Studholme NMI (MutualInfoService), row 1: 2 MI / (Hx + Hy)
+    (ZNCCService.compute_mi) -- of the rows of `df`; None when no row has its chips inside the
+    rasters.  One kr_mutual_info launch gives both; the second of the reference's two calls
+    (api/core.py:894-907) is served from the first."""
+    cols = np.empty((4, len(df)), np.float32)
+    for i, c in enumerate(("x0", "y0", "dx", "dy")):
+        cols[i] = df[c].to_numpy()
+    known = recall_mi(monitored, reference, cols)
+    if known is not None:
+        return known
+    inp = _score_inputs(df, monitored, reference)
+    if inp is None:
+        return None
+    pair = get_context(64, 64, 1024).mutual_info(*inp[:2], *inp[2]).cpu().numpy()
+    remember_mi(monitored, reference, cols, pair)
+    return pair
 
 
 class ZNCCService:
@@ -103,12 +122,8 @@ class ZNCCService:
         if len(df) == 0:
             score = Series(np.empty(0, np.float64), index=df.index, dtype=np.float64)
         else:
-            inp = _score_inputs(df, monitored, reference)
-            if inp is None:
-                score = Series(np.full(len(df), np.nan), index=df.index, dtype=np.float64)
-            else:
-                mi = get_context(64, 64, 1024).mutual_info(*inp[:2], *inp[2])
-                score = Series(mi[1].cpu().numpy(), index=df.index, dtype=np.float64)
+            pair = mutual_info_pair(df, monitored, reference)
+            score = Series(np.full(len(df), np.nan) if pair is None else pair[1], index=df.index, dtype=np.float64)
         monitored.clear_cache()
         reference.clear_cache()
         logger.info("NMI computation finish")
