@@ -105,6 +105,10 @@ __device__ __noinline__ void est_contribute(uint32_t *__restrict__ ghist, KrDevS
     __syncwarp();
     for (int k = lane; k < n; k += 32)
         atomicAdd(&ghist[est_bin((uint32_t)(cbuf[k] >> 32))], 1u);
+    // ... and a second count once they have landed: the scanner starts when enough rows are IN
+    __threadfence();
+    __syncwarp();
+    if (lane == 0) atomicAdd(&st->fa_rows_in, (uint32_t)rows);
 }
 
 // Running cut, the scanner: one extra warp of the grid (block (0, 0), dispatched first) waits until
@@ -115,18 +119,26 @@ __device__ __noinline__ void est_scanner(const uint32_t *ghist, KrDevStats *st, 
                                          float need_per_row, uint32_t n_workers, int lane)
 {
     constexpr unsigned FULL = 0xffffffffu;
+    // wait until the histogram holds the candidates of `trigger_rows` row pieces, then (the workers
+    // of a wave contribute in a burst) until the contributions under way have landed too, within
+    // reason; give up only when every worker is done and the sample is still too small
     uint32_t rows = 0;
-    for (;;) {
-        uint32_t done = 0;
+    for (int spins = 0;;) {
+        uint32_t in = 0, done = 0;
         if (lane == 0) {
             rows = *((volatile uint32_t *)&st->fa_rows);
+            in = *((volatile uint32_t *)&st->fa_rows_in);
             done = *((volatile uint32_t *)&st->fa_done);
         }
         rows = __shfl_sync(FULL, rows, 0);
+        in = __shfl_sync(FULL, in, 0);
         done = __shfl_sync(FULL, done, 0);
-        if (rows >= trigger_rows) break;
-        if (done >= n_workers) return;                       // small image: no estimate
-        __nanosleep(500);
+        if (in >= trigger_rows && (in == rows || ++spins > 12)) break;
+        if (done >= n_workers) {
+            if (in < trigger_rows) return;                   // small image: no estimate
+            break;
+        }
+        __nanosleep(400);
     }
     uint32_t bits = 0;
     for (int attempt = 0; attempt < 64; attempt++) {
@@ -163,9 +175,16 @@ __device__ __noinline__ void est_scanner(const uint32_t *ghist, KrDevStats *st, 
         uint32_t rows_now = 0;
         if (lane == 0) rows_now = *((volatile uint32_t *)&st->fa_rows);
         rows_now = __shfl_sync(FULL, rows_now, 0);
-        if (bits == 0 || (float)found >= need_per_row * (float)rows_now) break;
+        if (bits != 0 && (float)found >= need_per_row * (float)rows_now) break;
+        // too few candidates in sight for the rows counted: contributions still under way (look
+        // again) -- or, with nothing under way, an image without that many candidates (no estimate)
+        uint32_t in_now = 0;
+        if (lane == 0) in_now = *((volatile uint32_t *)&st->fa_rows_in);
+        in_now = __shfl_sync(FULL, in_now, 0);
+        if (bits == 0 && in_now == rows_now) break;
         rows = rows_now;
         bits = 0;
+        __nanosleep(400);
     }
     if (lane == 0 && bits) atomicExch(&st->cut_est_bits, bits);
 }

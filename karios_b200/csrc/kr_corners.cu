@@ -870,7 +870,7 @@ __global__ void k_clear_counts(KrDevStats *st)
     st->lmax_enc = st->umax_enc = KR_ENC_NEG_INF;
     st->n_maxlist = st->n_exact = 0;
     st->cut_applied = st->fast_mode = st->fast_fallback = 0;
-    st->cut_est_bits = st->fa_rows = st->fa_skipped = st->fa_done = 0;
+    st->cut_est_bits = st->fa_rows = st->fa_skipped = st->fa_done = st->fa_rows_in = 0;
 }
 
 __global__ void k_set_fast_mode(KrDevStats *st) { st->fast_mode = 1; }

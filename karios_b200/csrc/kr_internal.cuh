@@ -38,7 +38,8 @@ struct KrDevStats {
     uint32_t nms_pending[16];           // multi-launch NMS: candidates left undecided by round r
     uint32_t fa_skipped;                // tier 1: warp-rows ruled out as a whole by the running cut
     uint32_t fa_done;                   // tier 1: worker blocks that have finished
-    uint32_t pad2[2];
+    uint32_t fa_rows_in;                // tier 1: warp-rows whose candidates have LANDED in the histogram
+    uint32_t pad2[1];
 };
 
 struct kr_ctx {
