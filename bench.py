@@ -359,7 +359,9 @@ def cuda_arm(args):
     n_z = int((sm.rows.f32[4, : st.n_kept] >= 0.4).sum().item())
     sb = stage_bytes(P, st.n_candidates, st.n_corners, n_z)
     stages = {k: {"ms": round(acc[k], 4), "alg_bytes": sb[k],
-                  "gbs": round(sb[k] / (acc[k] * 1e6), 1) if acc[k] > 0 else None} for k in acc}
+                  "gbs": round(sb[k] / (acc[k] * 1e6), 1) if acc[k] > 0 else None,
+                  "frac_of_hbm_peak": round(sb[k] / (acc[k] * 1e6) / hbm_peak, 4) if acc[k] > 0 and sb[k] else None}
+              for k in acc}
     dom = max(acc, key=lambda k: acc[k])
     achieved = sb[dom] / (acc[dom] * 1e6) if acc[dom] > 0 else 0.0
     traffic, traffic_src = None, None
