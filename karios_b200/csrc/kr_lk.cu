@@ -658,6 +658,20 @@ k_lk_single(KrLkArgs A, const float *__restrict__ p0, int n, const int32_t *d_co
     }
 }
 
+// The windows a point is going to read -> L2, one row per lane (0.423 -> 0.416 ms on the S2 pair;
+// an L2 hit instead of a DRAM access when the template build reaches the row).  Rows of a window are
+// 26 - 30 bytes wide and start at any byte: two sectors per row.
+__device__ __forceinline__ void lk_prefetch(const uint8_t *__restrict__ img, int64_t pitch, int w, int h, float cx,
+                                            float cy, int half_w, int lane)
+{
+    const int x = (int)cx - half_w, y = (int)cy - half_w + lane;
+    if (lane <= 2 * half_w && y >= 0 && y < h && x >= 0 && x + 2 * half_w < w) {
+        const uint8_t *p = img + (int64_t)y * pitch + x;
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(p + 2 * half_w));
+    }
+}
+
 // forward (ref -> mon), backward (mon -> ref) from the forward result, then the
 // back-check of klt.py:142-144: d = max|p0 - p0r|, keep = d < 0.1 (float32).
 template <int WIN>
@@ -676,6 +690,13 @@ k_lk_roundtrip(KrLkArgs A, const float *__restrict__ p0, int n_cap, const uint32
         const float x0 = p0[2 * i], y0 = p0[2 * i + 1];
         float x1, y1, xr, yr, e;
         uint8_t st;
+        // the forward pass reads the reference and the monitored window at every level around the
+        // point (the displacement is a fraction of the window); the backward pass finds them cached
+        for (int l = A.levels; l >= 0; l--) {
+            const float sc = 1.f / (float)(1 << l);
+            lk_prefetch(A.img[0][l], A.pitch[0][l], A.w[l], A.h[l], x0 * sc, y0 * sc, 15, lane);
+            lk_prefetch(A.img[1][l], A.pitch[1][l], A.w[l], A.h[l], x0 * sc, y0 * sc, 15, lane);
+        }
         lk_track<WIN, false>(A, 0, x0, y0, x1, y1, st, e, sT, sJ, lane);
         lk_track<WIN, false>(A, 1, x1, y1, xr, yr, st, e, sT, sJ, lane);
         if (lane == 0) {
